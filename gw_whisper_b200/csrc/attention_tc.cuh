@@ -1,0 +1,281 @@
+// Fused non-causal multi-head self-attention for the Whisper encoder on tcgen05 / TMEM (sm_100a).
+// Reference math: HF modeling_whisper.py:215-238 (eager_attention_forward, scaling=1.0, no mask,
+// no dropout) with q pre-scaled by head_dim^-0.5 (:310) -- the scale is folded into W_q / b_q at
+// model-load time, so this kernel computes softmax(Q K^T) V per (det-window, head).
+//
+// Layout: qkv [Bt, T, 3*d] bf16 (q | k | v, head h at columns h*64), out [Bt, T, d] bf16.
+// One CTA = one (det-window, head, pair of 128-row query tiles); it streams the T keys in 128-row
+// K/V tiles through a 3-stage TMA ring.
+//   S_t = Q_t K_j^T     tcgen05.mma SS, M=128 N=128 K=64, accumulator in TMEM (fp32)
+//   softmax             two warpgroups (one per query tile), one thread per row, online max with
+//                       lazy rescale (only when the running max grows by > 2^8), exp2 on MUFU
+//   P_t -> TMEM (bf16)  tcgen05.st, then O_t += P_t V_j as tcgen05.mma TS (A from TMEM, V is the
+//                       MN-major B operand straight from its TMA tile), M=128 N=64 K=128
+// TMEM map (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
+// Warps: WG0/WG1 = softmax for query tile 0/1, WG2 = {w8: TMA producer, w9: MMA issuer + TMEM alloc}.
+#pragma once
+#include "ptx.cuh"
+
+namespace gww {
+
+struct AttnParams {
+  int T;        // tokens per det-window (1500)
+  int d_model;  // 384 / 512 / 768
+  int nkv;      // ceil(T / 128)
+};
+
+constexpr int kAttnStages = 3;
+constexpr int kAttnSmemBytes = 32768 + kAttnStages * 2 * 16384 + 256;
+
+__global__ void __launch_bounds__(384, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} box {64,128,1}
+                    const __grid_constant__ CUtensorMap tmO,    // {d, T, Bt}  box {64,32,1}
+                    const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("gww: attention dynamic smem base not 1024-aligned (0x%x)\n", smem_u32(smem));
+    __trap();
+  }
+  uint8_t* q_s = smem;                                  // 2 x 16 KB (later: O staging)
+  uint8_t* k_s = smem + 32768;                          // kAttnStages x 16 KB
+  uint8_t* v_s = k_s + kAttnStages * 16384;             // kAttnStages x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + kAttnStages * 16384);
+  const uint32_t bar_q = smem_u32(bars);                // 1
+  const uint32_t bar_kfull = bar_q + 8;                 // kAttnStages
+  const uint32_t bar_kempty = bar_kfull + 8 * kAttnStages;
+  const uint32_t bar_vfull = bar_kempty + 8 * kAttnStages;
+  const uint32_t bar_vempty = bar_vfull + 8 * kAttnStages;
+  const uint32_t bar_sfull = bar_vempty + 8 * kAttnStages;  // 2
+  const uint32_t bar_pfull = bar_sfull + 16;                // 2
+  const uint32_t bar_ofull = bar_pfull + 16;                // 2
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 1 + 4 * kAttnStages + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
+  const int qpair = blockIdx.x, head = blockIdx.y, bi = blockIdx.z;
+  const int q0 = qpair * 256;
+  const int nkv = p.nkv;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmO);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < kAttnStages; ++i) {
+      mbar_init(bar_kfull + 8 * i, 1);
+      mbar_init(bar_kempty + 8 * i, 1);
+      mbar_init(bar_vfull + 8 * i, 1);
+      mbar_init(bar_vempty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_sfull + 8 * i, 1);
+      mbar_init(bar_pfull + 8 * i, 128);
+      mbar_init(bar_ofull + 8 * i, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc<512>(smem_u32(tmem_ptr_s));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (wg == 2) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (warp == 8 && lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_arrive_expect_tx(bar_q, 32768);
+      tma_load_3d(smem_u32(q_s), &tmQKV, bar_q, head * 64, q0, bi);
+      tma_load_3d(smem_u32(q_s + 16384), &tmQKV, bar_q, head * 64, q0 + 128, bi);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(bar_kempty + 8 * stage, phase ^ 1);
+        mbar_arrive_expect_tx(bar_kfull + 8 * stage, 16384);
+        tma_load_3d(smem_u32(k_s + stage * 16384), &tmQKV, bar_kfull + 8 * stage,
+                    p.d_model + head * 64, j * 128, bi);
+        mbar_wait(bar_vempty + 8 * stage, phase ^ 1);
+        mbar_arrive_expect_tx(bar_vfull + 8 * stage, 16384);
+        tma_load_3d(smem_u32(v_s + stage * 16384), &tmQKV, bar_vfull + 8 * stage,
+                    2 * p.d_model + head * 64, j * 128, bi);
+        if (++stage == kAttnStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 9 && lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t kIdescS = make_idesc_bf16(128, 128, 0);
+      constexpr uint32_t kIdescO = make_idesc_bf16(128, 64, 1);   // V is MN-major
+      const uint32_t tS[2] = {tmem_base + 0u, tmem_base + 128u};
+      const uint32_t tP[2] = {tmem_base + 256u, tmem_base + 320u};
+      const uint32_t tO[2] = {tmem_base + 384u, tmem_base + 448u};
+      const uint64_t qdesc[2] = {make_sw128_desc(smem_u32(q_s)),
+                                 make_sw128_desc(smem_u32(q_s + 16384))};
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kfull, 0);
+      tc_fence_after();
+      {
+        const uint64_t kdesc = make_sw128_desc(smem_u32(k_s));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
+          umma_commit(bar_sfull + 8 * t);
+        }
+        umma_commit(bar_kempty);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == kAttnStages) { nstage = 0; nphase ^= 1; }
+        const bool has_next = (j + 1 < nkv);
+        mbar_wait(bar_vfull + 8 * stage, phase);
+        if (has_next) mbar_wait(bar_kfull + 8 * nstage, nphase);
+        const uint64_t vdesc = make_sw128_desc(smem_u32(v_s + stage * 16384));
+        const uint64_t kdesc = make_sw128_desc(smem_u32(k_s + nstage * 16384));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(bar_pfull + 8 * t, j & 1);
+          tc_fence_after();
+          // O_t (+)= P_t V_j : 8 K-steps of 16 keys; P advances 8 TMEM columns (16 bf16),
+          // V advances 16 rows x 128 B = 2048 B (=> +128 in the descriptor address field).
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_ts(tO[t], tP[t] + 8 * k, vdesc + 128 * k, kIdescO, (j | k) ? 1u : 0u);
+          if (!has_next) umma_commit(bar_ofull + 8 * t);
+          if (has_next) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
+            umma_commit(bar_sfull + 8 * t);
+          }
+        }
+        umma_commit(bar_vempty + 8 * stage);
+        if (has_next) umma_commit(bar_kempty + 8 * nstage);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int t = wg;                           // query tile handled by this warpgroup
+    const int wq = warp & 3;                    // TMEM lane quarter
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + t * 128;
+    const uint32_t tP = tmem_base + lane_off + 256 + t * 64;
+    const uint32_t tO = tmem_base + lane_off + 384 + t * 64;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m_used = 0.f, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(bar_sfull + 8 * t, j & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+      tmem_ld32(tS + 0, s[0]);
+      tmem_ld32(tS + 32, s[1]);
+      tmem_ld32(tS + 64, s[2]);
+      tmem_ld32(tS + 96, s[3]);
+      tmem_wait_ld();
+      const int valid = p.T - j * 128;          // keys [0, valid) of this tile exist
+      if (valid < 128) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+      }
+      float mt0 = -INFINITY, mt1 = -INFINITY, mt2 = -INFINITY, mt3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mt0 = fmaxf(mt0, __uint_as_float(s[0][i]));
+        mt1 = fmaxf(mt1, __uint_as_float(s[1][i]));
+        mt2 = fmaxf(mt2, __uint_as_float(s[2][i]));
+        mt3 = fmaxf(mt3, __uint_as_float(s[3][i]));
+      }
+      const float mt = fmaxf(fmaxf(mt0, mt1), fmaxf(mt2, mt3));
+      if (j == 0) {
+        m_used = mt;
+      } else {
+        // lazy rescale: exact (same algebra as online softmax), but skipped while the stale max
+        // keeps exp2 arguments <= 8.
+        const bool need = (mt - m_used) * kLog2e > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float sc = need ? fast_exp2((m_used - mt) * kLog2e) : 1.0f;
+          uint32_t o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(tO + h * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+            tmem_st32(tO + h * 32, o);
+          }
+          tmem_wait_st();
+          l *= sc;
+          if (need) m_used = mt;
+        }
+      }
+      const float mneg = -m_used * kLog2e;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c0 = h * 64 + 2 * i;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), kLog2e, mneg));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), kLog2e, mneg));
+          l0 += p0;
+          l1 += p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st32(tP + h * 32, pk);
+      }
+      l += l0 + l1;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_pfull + 8 * t);
+    }
+    // ---- epilogue: O_t / l -> bf16 -> swizzled staging (the dead Q_t buffer) -> TMA store
+    mbar_wait(bar_ofull + 8 * t, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    uint32_t o0[32], o1[32];
+    tmem_ld32(tO, o0);
+    tmem_ld32(tO + 32, o1);
+    tmem_wait_ld();
+    uint8_t* stg = q_s + t * 16384 + wq * 4096;
+    uint8_t* sb = stg + lane * 128;
+#pragma unroll
+    for (int jc = 0; jc < 8; ++jc) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = jc * 8 + e * 2;
+        const float a0 = __uint_as_float(col < 32 ? o0[col & 31] : o1[col & 31]) * inv_l;
+        const float a1 = __uint_as_float(col < 32 ? o0[(col + 1) & 31] : o1[(col + 1) & 31]) * inv_l;
+        pk[e] = pack_bf16x2(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(sb + ((jc ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&tmO, smem_u32(stg), head * 64, q0 + t * 128 + wq * 32, bi);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace gww

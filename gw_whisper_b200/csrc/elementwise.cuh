@@ -1,0 +1,186 @@
+// Bandwidth-bound helpers of the encoder path: LayerNorm (HF modeling_whisper.py:393,403,643),
+// the pooled MLP classifier heads (MLGWSC-1/inference.py:371-382, Signal_vs_Noise/src/model.py:9-20,
+// 35-47, Glitch_classification/src/model.py:10-21) and the threshold -> trigger compaction that
+// replaces the per-element python loop at MLGWSC-1/inference.py:484-487.
+#pragma once
+#include "ptx.cuh"
+
+namespace gww {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (d = 128*NV), one warp per row, two-pass in registers.
+// in  : f32, row i is read at in + (in_off + i*in_stride) * d
+// out : bf16 or f32, dense [rows, d]
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ in, OutT* __restrict__ out,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, long rows,
+                 long in_off, long in_stride, float eps) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(in + (in_off + row * in_stride) * D);
+  float4 v[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = src[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    const float o0 = fmaf(v[i].x * rstd, g.x, b.x), o1 = fmaf(v[i].y * rstd, g.y, b.y);
+    const float o2 = fmaf(v[i].z * rstd, g.z, b.z), o3 = fmaf(v[i].w * rstd, g.w, b.w);
+    if constexpr (sizeof(OutT) == 2) {
+      uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      reinterpret_cast<uint2*>(out + row * D)[lane + 32 * i] = pk;
+    } else {
+      reinterpret_cast<float4*>(out + row * D)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
+// mean over tokens (use_last_token=False branch, MLGWSC-1/inference.py:390): hs [Bt, T, d] f32
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256)
+mean_pool_kernel(const float* __restrict__ hs, float* __restrict__ out, int T, int d) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += hs[(static_cast<size_t>(b) * T + t) * d + c];
+    out[static_cast<size_t>(b) * d + c] = acc / static_cast<float>(T);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pooled classifier head: x [B, in0] f32 -> Linear(+ReLU) x (L-1) -> Linear -> optional softmax.
+// kHeadWPB windows share one CTA so each weight row is read once per 8 windows; a warp owns an
+// output neuron and its lanes stride over the input (coalesced weight reads, shuffle reduce).
+constexpr int kHeadMaxLayers = 6;
+constexpr int kHeadWPB = 8;
+constexpr int kHeadMaxWidth = 1536;
+struct HeadParams {
+  int n_layers;
+  int dims[kHeadMaxLayers + 1];       // dims[0]=in, dims[i+1]=out of layer i
+  const float* w[kHeadMaxLayers];     // [out, in] row-major (nn.Linear)
+  const float* b[kHeadMaxLayers];
+  int softmax;                        // apply softmax over the last layer's outputs
+  int B;
+};
+
+__global__ void __launch_bounds__(512)
+head_mlp_kernel(const float* __restrict__ x, float* __restrict__ out, const HeadParams hp) {
+  extern __shared__ float hbuf[];                 // 2 x kHeadWPB x kHeadMaxWidth
+  float* cur = hbuf;
+  float* nxt = hbuf + kHeadWPB * kHeadMaxWidth;
+  const int w0 = blockIdx.x * kHeadWPB;
+  const int nw = min(kHeadWPB, hp.B - w0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int in0 = hp.dims[0];
+  for (int i = threadIdx.x; i < kHeadWPB * in0; i += blockDim.x) {
+    const int wdx = i / in0, c = i - wdx * in0;
+    cur[wdx * kHeadMaxWidth + c] = (wdx < nw) ? x[static_cast<size_t>(w0 + wdx) * in0 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int L = 0; L < hp.n_layers; ++L) {
+    const int din = hp.dims[L], dout = hp.dims[L + 1];
+    const bool last = (L == hp.n_layers - 1);
+    for (int j = warp; j < dout; j += nwarps) {
+      const float* wr = hp.w[L] + static_cast<size_t>(j) * din;
+      float acc[kHeadWPB];
+#pragma unroll
+      for (int q = 0; q < kHeadWPB; ++q) acc[q] = 0.f;
+      for (int i = lane; i < din; i += 32) {
+        const float wv = __ldg(wr + i);
+#pragma unroll
+        for (int q = 0; q < kHeadWPB; ++q) acc[q] = fmaf(wv, cur[q * kHeadMaxWidth + i], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < kHeadWPB; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+      if (lane == 0) {
+        const float bj = hp.b[L][j];
+#pragma unroll
+        for (int q = 0; q < kHeadWPB; ++q) {
+          float v = acc[q] + bj;
+          if (!last) v = fmaxf(v, 0.f);
+          nxt[q * kHeadMaxWidth + j] = v;
+        }
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  const int C = hp.dims[hp.n_layers];
+  if (threadIdx.x < nw) {
+    const float* r = cur + threadIdx.x * kHeadMaxWidth;
+    float* o = out + static_cast<size_t>(w0 + threadIdx.x) * C;
+    if (hp.softmax) {
+      float m = -INFINITY;
+      for (int c = 0; c < C; ++c) m = fmaxf(m, r[c]);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += expf(r[c] - m);
+      for (int c = 0; c < C; ++c) o[c] = expf(r[c] - m) / s;
+    } else {
+      for (int c = 0; c < C; ++c) o[c] = r[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered stream compaction of windows whose score (column 0 of out[B, C]) exceeds the threshold
+// (strictly greater, MLGWSC-1/inference.py:484). Single CTA, ballot scan: output order == window
+// order, so the host-side clustering sees the same sequence the reference's python loop builds.
+__global__ void __launch_bounds__(1024)
+threshold_compact_kernel(const float* __restrict__ out, int C, int n, float thr, long idx_base,
+                         long* __restrict__ trig_idx, float* __restrict__ trig_score,
+                         int* __restrict__ count, int capacity) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) base_s = *count;
+  __syncthreads();
+  for (int start = 0; start < n; start += 1024) {
+    const int i = start + threadIdx.x;
+    const float sc = (i < n) ? out[static_cast<size_t>(i) * C] : 0.f;
+    const bool keep = (i < n) && (sc > thr);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (keep && off < capacity) {
+      trig_idx[off] = idx_base + i;
+      trig_score[off] = sc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_tot[w];
+      base_s += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+
+}  // namespace gww

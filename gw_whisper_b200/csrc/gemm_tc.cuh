@@ -1,0 +1,331 @@
+// Persistent, warp-specialised bf16 GEMM on tcgen05 / TMEM fed by TMA (sm_100a).
+//
+//   C[b, r, n] = epilogue( sum_{tap, c} A[b, r*? + tap, c] * W[n, tap*Cpad + c] )
+//
+// One kernel serves every dense contraction of the Whisper encoder
+// (HF modeling_whisper.py:619-625 conv stem, :310/:331-332/:355 projections, :403-408 MLP):
+//   * A is read through a 4-D tensor map {C, P, R, Bt}: for a plain Linear P=1 and taps=1; for the
+//     k=3 convolutions the three taps are three row-shifted TMA boxes of the same (zero-row padded)
+//     activation, i.e. im2col is done by the TMA unit, never materialised.
+//   * W is [N, Ktot] bf16, K-major (nn.Linear layout), read through a 2-D map.
+//   * Accumulators live in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps
+//     the MMAs of tile i+1.
+//   * Epilogue warps read TMEM with tcgen05.ld, apply bias / GELU / residual / positional embedding,
+//     stage through 128B-swizzled shared memory and write with TMA stores (clipped at tensor edges).
+//
+// Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
+// w4..w7 = epilogue (TMEM lane quarter = warp_idx % 4).
+#pragma once
+#include "ptx.cuh"
+
+namespace gww {
+
+enum GemmEpilogue : int {
+  EPI_BIAS_BF16 = 0,       // out bf16 = acc + bias                      (QKV projection)
+  EPI_BIAS_GELU_BF16 = 1,  // out bf16 = gelu(acc + bias)                (conv1, fc1)
+  EPI_BIAS_RESID_F32 = 2,  // out f32  = resid + acc + bias              (out_proj, fc2; in-place ok)
+  EPI_BIAS_GELU_POS_F32 = 3  // out f32 = gelu(acc + bias) + pos[r, n]   (conv2 + embed_positions)
+};
+
+struct GemmParams {
+  int rows;          // output rows per batch entry (R)
+  int batch;         // Bt
+  int n;             // output features (multiple of 64)
+  int kb_per_tap;    // 64-wide K blocks per tap
+  int taps;          // 1 (Linear) or 3 (conv k=3)
+  int p_mod;         // P: tap -> (tap % P, tap / P) coordinates in dims 1 and 2 of the A map
+  const float* bias;   // [n] or nullptr
+  const float* resid;  // [batch*rows, n] f32 (EPI_BIAS_RESID_F32)
+  const float* pos;    // [rows, n] f32 (EPI_BIAS_GELU_POS_F32)
+};
+
+// erf-GELU, |err| < 2.5e-6 absolute (fit of -log2(erfc(z))/z, z=|v|/sqrt2 in [0,4], degree 5):
+// gelu(v) = 0.5 v (1 + sign(v) (1 - 2^(-z Q(z)))).   1 MUFU + ~12 FP32 ops.
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+  float z = fminf(fabsf(v) * 0.70710678118654752f, 4.0f);
+  float q = -0.00023341832275036722f;
+  q = fmaf(q, z, 0.0040274024941027164f);
+  q = fmaf(q, z, -0.03122980147600174f);
+  q = fmaf(q, z, 0.1495656669139862f);
+  q = fmaf(q, z, 0.9183619618415833f);
+  q = fmaf(q, z, 1.6279007196426392f);
+  float e = fast_exp2(-z * q);
+  float er = copysignf(1.0f - e, v);
+  float hv = 0.5f * v;
+  return fmaf(hv, er, hv);
+}
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 4 : 6);
+  static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 4 /*warps*/ * 2 /*bufs*/ * 4096;
+  static constexpr int kBiasBytes = 2 * 256 * 4;
+  static constexpr int kBarBytes = 128;
+  // dynamic smem is declared __align__(1024); no slack needed (checked at kernel entry)
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr bool kOutF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
+  constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("gww: gemm dynamic smem base not 1024-aligned (0x%x)\n", smem_u32(smem));
+    __trap();
+  }
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + kStages * S::kStageBytes;
+  float* bias_s = reinterpret_cast<float*>(staging + S::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + S::kBiasBytes);
+  // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_per_batch = (p.rows + 127) >> 7;
+  const int tiles_m = tiles_per_batch * p.batch;
+  const int tiles_n = (p.n + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.kb_per_tap * p.taps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kTmemCols>(smem_u32(tmem_ptr_s));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = tile / tiles_n;
+        const int n_idx = tile - m_idx * tiles_n;
+        const int b = m_idx / tiles_per_batch;
+        const int r0 = (m_idx - b * tiles_per_batch) << 7;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, S::kStageBytes);
+          const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
+          const int tap = kb / p.kb_per_tap;
+          const int kc = kb - tap * p.kb_per_tap;
+          tma_load_4d(sa, &tmA, full, kc * 64, tap % p.p_mod, r0 + tap / p.p_mod, b);
+          tma_load_2d(sa + S::kABytes, &tmB, full, kb * 64, n_idx * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
+          const uint64_t adesc = make_sw128_desc(sa);
+          const uint64_t bdesc = make_sw128_desc(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // +32 B per 16-element K step inside the 128B swizzle atom => +2 in the addr field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * as);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;            // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int et = threadIdx.x - 128;   // 0..127
+    uint8_t* my_staging = staging + ew * 8192;
+    int as = 0;
+    uint32_t aphase = 0;
+    int sbuf = 0;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int m_idx = tile / tiles_n;
+      const int n_idx = tile - m_idx * tiles_n;
+      const int b = m_idx / tiles_per_batch;
+      const int r0 = (m_idx - b * tiles_per_batch) << 7;
+      const int n0 = n_idx * BN;
+      const int r = r0 + ew * 32 + lane;      // this thread's output row inside the batch entry
+      const bool row_ok = r < p.rows;
+
+      // stage this tile's bias slice (double-buffered by tile parity; see barrier argument in
+      // one named barrier per tile is enough to order refills)
+      float* bias_t = bias_s + (tcount & 1) * 256;
+      for (int i = et; i < BN; i += 128) {
+        const int n = n0 + i;
+        bias_t[i] = (p.bias != nullptr && n < p.n) ? __ldg(p.bias + n) : 0.0f;
+      }
+      named_bar_sync(1, 128);
+
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+
+      if constexpr (!kOutF32) {
+        // bf16 output: 64 columns (128 B per row) per staging buffer
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_acc + c * 64, v0);
+          tmem_ld32(t_acc + c * 64 + 32, v1);
+          if (lane == 0) tma_store_wait_read<1>();   // staging[sbuf] no longer being read
+          __syncwarp();
+          tmem_wait_ld();
+          if (c == BN / 64 - 1) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * as);        // accumulator drained -> MMA may reuse it
+          }
+          uint8_t* sb = my_staging + sbuf * 4096 + lane * 128;
+          const float4* bs4 = reinterpret_cast<const float4*>(bias_t + c * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {              // 8 x 16 B chunks of this row
+            uint32_t pk[4];
+            const float4 bA = bs4[2 * j], bB = bs4[2 * j + 1];
+            const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = j * 8 + e * 2;
+              float a0 = __uint_as_float(col < 32 ? v0[col & 31] : v1[col & 31]);
+              float a1 = __uint_as_float(col < 32 ? v0[(col + 1) & 31] : v1[(col + 1) & 31]);
+              a0 += bv[e * 2];
+              a1 += bv[e * 2 + 1];
+              if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                a0 = gelu_erf_fast(a0);
+                a1 = gelu_erf_fast(a1);
+              }
+              pk[e] = pack_bf16x2(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(sb + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, smem_u32(my_staging + sbuf * 4096), n0 + c * 64, r0 + ew * 32, b);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+      } else {
+        // f32 output: 32 columns (128 B per row) per staging buffer
+        const size_t grow = static_cast<size_t>(b) * p.rows + r;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v0[32];
+          tmem_ld32(t_acc + c * 32, v0);
+          float add[32];
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            const float4* rp = reinterpret_cast<const float4*>(p.resid + grow * p.n + n0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = (row_ok && n0 + c * 32 < p.n) ? rp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+              add[4 * j] = t.x; add[4 * j + 1] = t.y; add[4 * j + 2] = t.z; add[4 * j + 3] = t.w;
+            }
+          } else {
+            const float4* pp = reinterpret_cast<const float4*>(
+                p.pos + static_cast<size_t>(row_ok ? r : 0) * p.n + (n0 + c * 32 < p.n ? n0 + c * 32 : 0));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t = __ldg(pp + j);
+              add[4 * j] = t.x; add[4 * j + 1] = t.y; add[4 * j + 2] = t.z; add[4 * j + 3] = t.w;
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          tmem_wait_ld();
+          if (c == BN / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * as);
+          }
+          uint8_t* sb = my_staging + sbuf * 4096 + lane * 128;
+          const float4* bs4 = reinterpret_cast<const float4*>(bias_t + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float o[4];
+            const float4 bA = bs4[j];
+            const float bv[4] = {bA.x, bA.y, bA.z, bA.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = j * 4 + e;
+              float a = __uint_as_float(v0[col]) + bv[e];
+              if constexpr (EPI == EPI_BIAS_GELU_POS_F32) a = gelu_erf_fast(a);
+              o[e] = a + add[col];
+            }
+            *reinterpret_cast<float4*>(sb + ((j ^ (lane & 7)) << 4)) =
+                make_float4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, smem_u32(my_staging + sbuf * 4096), n0 + c * 32, r0 + ew * 32, b);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace gww

@@ -1,0 +1,809 @@
+// C-ABI implementation (include/gww.h): host orchestration of the sm_100a kernels.
+// One process per GPU; all work is enqueued on the caller's stream; no allocation on the hot path.
+#include "../../include/gww.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "attention_tc.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+#include "logmel.cuh"
+
+using namespace gww;
+
+// ------------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(GWW_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+#define GWW_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != GWW_OK) return _r; \
+  } while (0)
+#define LAUNCH_CHECK()  \
+  do {                  \
+    ++g_launches;       \
+    CU_TRY(cudaGetLastError()); \
+  } while (0)
+
+extern "C" const char* gww_last_error(void) { return g_err.c_str(); }
+extern "C" const char* gww_version(void) { return "gw-whisper-b200 0.1 (sm_100a)"; }
+extern "C" long gww_launch_count(void) { return g_launches.load(); }
+
+static int g_num_sms = 0;
+extern "C" int gww_device_ok(void) {
+  if (g_num_sms > 0) return GWW_OK;   // one process per GPU: checked once
+  int dev = 0, count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(GWW_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+  }
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(GWW_ERR_NO_DEVICE, "device %s is sm_%d%d; kernels are built for sm_100a only",
+                prop.name, prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  return GWW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return GWW_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+    return fail(GWW_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return GWW_OK;
+}
+
+// dims/box are innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).
+static int make_map(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  GWW_TRY(get_encode());
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                        rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(GWW_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): rank=%d base=%p dims=[%llu,%llu,%llu,%llu] "
+                "strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+                (int)r, rank, base, (unsigned long long)dims[0],
+                (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0),
+                (unsigned long long)(rank > 3 ? dims[3] : 0),
+                (unsigned long long)(rank > 1 ? strides_bytes[0] : 0),
+                (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+                (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0],
+                rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  }
+  return GWW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------------
+struct GemmCall {
+  // A operand: 4-D view {C, P, R, Bt} of a bf16 activation
+  const void* a_base;
+  uint64_t a_dims[4];
+  uint64_t a_strides[3];
+  // W: [N, Ktot] bf16
+  const void* w_base;
+  int ktot;
+  // C: 3-D view {N, rows, batch}
+  void* c_base;
+  uint64_t c_strides[2];
+  GemmParams p;
+  int epi;
+  int block_n;
+};
+
+template <int BN, int EPI>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                         const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN>::kTotal));
+    attr_set = true;
+  }
+  const int tiles = ((p.rows + 127) / 128) * p.batch * ((p.n + BN - 1) / BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, 256, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, tmC, p);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+template <int BN>
+static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                          const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(a, b, c, p, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(a, b, c, p, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32>(a, b, c, p, s);
+    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32>(a, b, c, p, s);
+  }
+  return fail(GWW_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
+static int run_gemm(const GemmCall& g, cudaStream_t stream) {
+  if (g.p.n % 64 != 0) return fail(GWW_ERR_INVALID, "gemm: N=%d must be a multiple of 64", g.p.n);
+  if (g.ktot % 64 != 0) return fail(GWW_ERR_INVALID, "gemm: K=%d must be a multiple of 64", g.ktot);
+  const bool out_f32 = (g.epi == EPI_BIAS_RESID_F32 || g.epi == EPI_BIAS_GELU_POS_F32);
+  if (out_f32 && g.p.n % g.block_n != 0)
+    return fail(GWW_ERR_INVALID, "gemm: f32 epilogues need N %% block_n == 0 (N=%d)", g.p.n);
+  CUtensorMap tmA, tmB, tmC;
+  const uint32_t abox[4] = {64, 1, 128, 1};
+  GWW_TRY(make_map(&tmA, false, 4, g.a_base, g.a_dims, g.a_strides, abox));
+  const uint64_t wdims[2] = {(uint64_t)g.ktot, (uint64_t)g.p.n};
+  const uint64_t wstr[1] = {(uint64_t)g.ktot * 2};
+  const uint32_t wbox[2] = {64, (uint32_t)g.block_n};
+  GWW_TRY(make_map(&tmB, false, 2, g.w_base, wdims, wstr, wbox));
+  const uint64_t cdims[3] = {(uint64_t)g.p.n, (uint64_t)g.p.rows, (uint64_t)g.p.batch};
+  const uint32_t cbox[3] = {out_f32 ? 32u : 64u, 32, 1};
+  GWW_TRY(make_map(&tmC, out_f32, 3, g.c_base, cdims, g.c_strides, cbox));
+  switch (g.block_n) {
+    case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, tmC, g.p, stream);
+    case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, tmC, g.p, stream);
+    case 256: return launch_gemm_bn<256>(g.epi, tmA, tmB, tmC, g.p, stream);
+  }
+  return fail(GWW_ERR_INVALID, "gemm: block_n must be 128, 192 or 256 (got %d)", g.block_n);
+}
+
+// plain Linear: C[M,N] = epi(A[M,K] W[N,K]^T)
+static int run_linear(const void* A, const void* W, void* C, const float* bias, const float* resid,
+                      long M, int N, int K, int epi, int block_n, cudaStream_t stream) {
+  GemmCall g{};
+  g.a_base = A;
+  g.a_dims[0] = K; g.a_dims[1] = 1; g.a_dims[2] = M; g.a_dims[3] = 1;
+  g.a_strides[0] = (uint64_t)K * 2; g.a_strides[1] = (uint64_t)K * 2; g.a_strides[2] = (uint64_t)M * K * 2;
+  g.w_base = W;
+  g.ktot = K;
+  g.c_base = C;
+  const bool out_f32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_GELU_POS_F32);
+  const uint64_t esz = out_f32 ? 4 : 2;
+  g.c_strides[0] = (uint64_t)N * esz;
+  g.c_strides[1] = (uint64_t)M * N * esz;
+  g.p.rows = (int)M; g.p.batch = 1; g.p.n = N; g.p.kb_per_tap = K / 64; g.p.taps = 1; g.p.p_mod = 1;
+  g.p.bias = bias; g.p.resid = resid; g.p.pos = nullptr;
+  g.epi = epi;
+  g.block_n = block_n;
+  return run_gemm(g, stream);
+}
+
+static int pick_block_n(int n) {
+  if (n % 256 == 0) return 256;
+  if (n % 192 == 0) return 192;
+  return 128;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention / layernorm launchers
+// ------------------------------------------------------------------------------------------------
+static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaStream_t stream) {
+  if (d % 64 != 0) return fail(GWW_ERR_INVALID, "attention: d_model %% 64 != 0");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kAttnSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmO;
+  const uint64_t qd[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)n};
+  const uint64_t qs[2] = {(uint64_t)6 * d, (uint64_t)T * 6 * d};
+  const uint32_t qb[3] = {64, 128, 1};
+  GWW_TRY(make_map(&tmQ, false, 3, qkv, qd, qs, qb));
+  const uint64_t od[3] = {(uint64_t)d, (uint64_t)T, (uint64_t)n};
+  const uint64_t os[2] = {(uint64_t)2 * d, (uint64_t)T * 2 * d};
+  const uint32_t ob[3] = {64, 32, 1};
+  GWW_TRY(make_map(&tmO, false, 3, out, od, os, ob));
+  AttnParams ap;
+  ap.T = T; ap.d_model = d; ap.nkv = (T + 127) / 128;
+  for (long z0 = 0; z0 < n; z0 += 32768) {   // gridDim.z limit
+    const long nz = (n - z0 < 32768) ? n - z0 : 32768;
+    if (z0 != 0) return fail(GWW_ERR_INVALID, "attention: more than 32768 det-windows per call");
+    dim3 grid((T + 255) / 256, d / 64, (unsigned)nz);
+    attention_tc_kernel<<<grid, 384, kAttnSmemBytes, stream>>>(tmQ, tmO, ap);
+    LAUNCH_CHECK();
+  }
+  return GWW_OK;
+}
+
+template <typename OutT>
+static int run_ln_t(const float* x, OutT* out, const float* g, const float* b, long rows, int d,
+                    long in_off, long in_stride, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const float eps = 1e-5f;
+  switch (d) {
+    case 384: layernorm_kernel<3, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
+    case 512: layernorm_kernel<4, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
+    case 768: layernorm_kernel<6, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
+    case 1024: layernorm_kernel<8, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
+    case 1280: layernorm_kernel<10, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
+    default: return fail(GWW_ERR_INVALID, "layernorm: unsupported d=%d", d);
+  }
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// log-mel tables
+// ------------------------------------------------------------------------------------------------
+static LogmelTables g_lm{};
+static bool g_lm_ready = false;
+static std::mutex g_lm_mu;
+
+static double hz_to_mel(double f) {
+  return (f >= 1000.0) ? 15.0 + std::log(f / 1000.0) * (27.0 / std::log(6.4)) : 3.0 * f / 200.0;
+}
+static double mel_to_hz(double m) {
+  return (m >= 15.0) ? 1000.0 * std::exp((std::log(6.4) / 27.0) * (m - 15.0)) : 200.0 * m / 3.0;
+}
+
+template <typename T>
+static int upload(const std::vector<T>& h, const T** dptr) {
+  T* d = nullptr;
+  CU_TRY(cudaMalloc(&d, h.size() * sizeof(T)));
+  CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = d;
+  return GWW_OK;
+}
+
+static int logmel_tables_init() {
+  std::lock_guard<std::mutex> lk(g_lm_mu);
+  if (g_lm_ready) return GWW_OK;
+  const double PI = 3.14159265358979323846;
+  std::vector<double2> t2048(1024), t16000(16000), t125(125), t400(400);
+  for (int j = 0; j < 1024; ++j) t2048[j] = make_double2(std::cos(2 * PI * j / 2048), -std::sin(2 * PI * j / 2048));
+  for (int j = 0; j < 16000; ++j) t16000[j] = make_double2(std::cos(2 * PI * j / 16000), std::sin(2 * PI * j / 16000));
+  for (int j = 0; j < 125; ++j) t125[j] = make_double2(std::cos(2 * PI * j / 125), std::sin(2 * PI * j / 125));
+  for (int j = 0; j < 400; ++j) t400[j] = make_double2(std::cos(2 * PI * j / 400), std::sin(2 * PI * j / 400));
+  // slaney mel filter bank, 201 bins x 80 filters (HF audio_utils.mel_filter_bank,
+  // feature_extraction_whisper.py:94-102): triangular, slaney area normalisation
+  std::vector<double> hz(82);
+  const double mlo = hz_to_mel(0.0), mhi = hz_to_mel(8000.0);
+  for (int i = 0; i < 82; ++i) hz[i] = mel_to_hz(mlo + (mhi - mlo) * i / 81.0);
+  std::vector<int> lo(80), cnt(80), off(80);
+  std::vector<double> wts;
+  for (int m = 0; m < 80; ++m) {
+    const double enorm = 2.0 / (hz[m + 2] - hz[m]);
+    int first = -1, last = -1;
+    std::vector<double> row(201);
+    for (int k = 0; k < 201; ++k) {
+      const double f = 8000.0 * k / 200.0;
+      const double down = (f - hz[m]) / (hz[m + 1] - hz[m]);
+      const double up = (hz[m + 2] - f) / (hz[m + 2] - hz[m + 1]);
+      const double v = std::fmax(0.0, std::fmin(down, up)) * enorm;
+      row[k] = v;
+      if (v > 0.0) { if (first < 0) first = k; last = k; }
+    }
+    if (first < 0) { first = 0; last = -1; }
+    lo[m] = first; cnt[m] = last - first + 1; off[m] = (int)wts.size();
+    for (int k = first; k <= last; ++k) wts.push_back(row[k]);
+  }
+  if (wts.empty()) wts.push_back(0.0);
+  GWW_TRY(upload(t2048, &g_lm.tw2048));
+  GWW_TRY(upload(t16000, &g_lm.tw16000));
+  GWW_TRY(upload(t125, &g_lm.tw125));
+  GWW_TRY(upload(t400, &g_lm.tw400));
+  GWW_TRY(upload(lo, &g_lm.mel_lo));
+  GWW_TRY(upload(cnt, &g_lm.mel_cnt));
+  GWW_TRY(upload(off, &g_lm.mel_off));
+  GWW_TRY(upload(wts, &g_lm.mel_w));
+  CU_TRY(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmSmemBytes));
+  g_lm_ready = true;
+  return GWW_OK;
+}
+
+// strain addressing: det-window w = b*D + i reads strain + b*win_stride + i*det_stride
+__global__ void __launch_bounds__(256)
+gather_windows_kernel(const float* __restrict__ strain, float* __restrict__ out, long n_dw, int D,
+                      long win_stride, long det_stride) {
+  const long w = blockIdx.x;
+  if (w >= n_dw) return;
+  const float* src = strain + (w / D) * win_stride + (w % D) * det_stride;
+  for (int i = threadIdx.x; i < 2048; i += 256) out[w * 2048 + i] = src[i];
+}
+
+static int run_logmel(const float* strain_contig, long n, float* out_f32, __nv_bfloat16* out_tm,
+                      cudaStream_t stream) {
+  GWW_TRY(logmel_tables_init());
+  const int grid = (int)(n < (long)g_num_sms ? n : (long)g_num_sms);
+  logmel_kernel<<<grid, kLmThreads, kLmSmemBytes, stream>>>(strain_contig, n, out_f32, out_tm, g_lm);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct LayerDev {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
+  float *qkv_b, *o_b, *fc1_b, *fc2_b;
+};
+struct gww_model {
+  gww_encoder_config_t cfg;
+  __nv_bfloat16 *conv1_w, *conv2_w;   // [d, 384], [d, 3d]
+  float *conv1_b, *conv2_b, *pos_emb, *lnp_g, *lnp_b;
+  std::vector<LayerDev> layers;
+  std::vector<void*> owned;
+  bool has_head = false;
+  HeadParams head{};
+};
+
+static int dev_f32(gww_model* m, const float* h, size_t n, float** out) {
+  float* d = nullptr;
+  CU_TRY(cudaMalloc(&d, n * sizeof(float)));
+  m->owned.push_back(d);
+  if (h) CU_TRY(cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice));
+  else CU_TRY(cudaMemset(d, 0, n * sizeof(float)));
+  *out = d;
+  return GWW_OK;
+}
+static int dev_bf16(gww_model* m, const std::vector<float>& h, __nv_bfloat16** out) {
+  std::vector<__nv_bfloat16> hb(h.size());
+  for (size_t i = 0; i < h.size(); ++i) hb[i] = __float2bfloat16(h[i]);
+  __nv_bfloat16* d = nullptr;
+  CU_TRY(cudaMalloc(&d, hb.size() * sizeof(__nv_bfloat16)));
+  m->owned.push_back(d);
+  CU_TRY(cudaMemcpy(d, hb.data(), hb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  *out = d;
+  return GWW_OK;
+}
+
+// W' = diag(m / ||W0 + s B A||_row) (W0 + s B A)   (PEFT 0.12 DoRA merge; fp32 with f64 norms)
+static void dora_merge(const float* W0, int dout, int din, const gww_dora_t& a, std::vector<float>& out) {
+  out.assign(W0, W0 + (size_t)dout * din);
+  if (a.lora_A == nullptr || a.lora_B == nullptr || a.magnitude == nullptr || a.r <= 0) return;
+  for (int o = 0; o < dout; ++o) {
+    float* row = out.data() + (size_t)o * din;
+    for (int r = 0; r < a.r; ++r) {
+      const float br = a.scale * a.lora_B[(size_t)o * a.r + r];
+      const float* ar = a.lora_A + (size_t)r * din;
+      for (int i = 0; i < din; ++i) row[i] += br * ar[i];
+    }
+    double nrm = 0.0;
+    for (int i = 0; i < din; ++i) nrm += (double)row[i] * row[i];
+    const float sc = (float)((double)a.magnitude[o] / std::sqrt(nrm));
+    for (int i = 0; i < din; ++i) row[i] *= sc;
+  }
+}
+
+extern "C" int gww_model_create(const gww_encoder_config_t* cfg, const gww_encoder_weights_t* w,
+                                gww_model_t** out) {
+  if (!cfg || !w || !out) return fail(GWW_ERR_INVALID, "model_create: null argument");
+  GWW_TRY(gww_device_ok());
+  const int d = cfg->d_model, f = cfg->ffn_dim, L = cfg->n_layers;
+  if (d % 128 != 0 || cfg->n_heads * 64 != d || f % 64 != 0 || L <= 0)
+    return fail(GWW_ERR_INVALID, "model_create: unsupported geometry d=%d heads=%d ffn=%d layers=%d",
+                d, cfg->n_heads, f, L);
+  gww_model* m = new gww_model();
+  m->cfg = *cfg;
+  int rc = GWW_OK;
+  auto guard = [&](int r) { if (r != GWW_OK && rc == GWW_OK) rc = r; return r; };
+  {
+    std::vector<float> p((size_t)d * 384, 0.f);
+    for (int co = 0; co < d; ++co)
+      for (int ci = 0; ci < 80; ++ci)
+        for (int t = 0; t < 3; ++t) p[(size_t)co * 384 + t * 128 + ci] = w->conv1_w[((size_t)co * 80 + ci) * 3 + t];
+    guard(dev_bf16(m, p, &m->conv1_w));
+    std::vector<float> p2((size_t)d * 3 * d);
+    for (int co = 0; co < d; ++co)
+      for (int ci = 0; ci < d; ++ci)
+        for (int t = 0; t < 3; ++t) p2[(size_t)co * 3 * d + (size_t)t * d + ci] = w->conv2_w[((size_t)co * d + ci) * 3 + t];
+    guard(dev_bf16(m, p2, &m->conv2_w));
+  }
+  guard(dev_f32(m, w->conv1_b, d, &m->conv1_b));
+  guard(dev_f32(m, w->conv2_b, d, &m->conv2_b));
+  guard(dev_f32(m, w->pos_emb, (size_t)GWW_N_CTX * d, &m->pos_emb));
+  guard(dev_f32(m, w->ln_post_g, d, &m->lnp_g));
+  guard(dev_f32(m, w->ln_post_b, d, &m->lnp_b));
+  m->layers.resize(L);
+  for (int l = 0; l < L && rc == GWW_OK; ++l) {
+    const gww_layer_weights_t& lw = w->layers[l];
+    LayerDev& ld = m->layers[l];
+    guard(dev_f32(m, lw.ln1_g, d, &ld.ln1_g));
+    guard(dev_f32(m, lw.ln1_b, d, &ld.ln1_b));
+    guard(dev_f32(m, lw.ln2_g, d, &ld.ln2_g));
+    guard(dev_f32(m, lw.ln2_b, d, &ld.ln2_b));
+    std::vector<float> q, k, v, o;
+    dora_merge(lw.q_w, d, d, lw.dora_q, q);
+    dora_merge(lw.k_w, d, d, lw.dora_k, k);
+    dora_merge(lw.v_w, d, d, lw.dora_v, v);
+    dora_merge(lw.o_w, d, d, lw.dora_o, o);
+    std::vector<float> qkv((size_t)3 * d * d), qkvb((size_t)3 * d, 0.f);
+    const float qs = 0.125f;  // head_dim^-0.5, exact in bf16; applied after bias in the reference (:310)
+    for (size_t i = 0; i < (size_t)d * d; ++i) {
+      qkv[i] = q[i] * qs;
+      qkv[(size_t)d * d + i] = k[i];
+      qkv[(size_t)2 * d * d + i] = v[i];
+    }
+    for (int i = 0; i < d; ++i) {
+      qkvb[i] = (lw.q_b ? lw.q_b[i] : 0.f) * qs;
+      qkvb[2 * d + i] = lw.v_b ? lw.v_b[i] : 0.f;
+    }
+    guard(dev_bf16(m, qkv, &ld.qkv_w));
+    guard(dev_f32(m, qkvb.data(), 3 * d, &ld.qkv_b));
+    guard(dev_bf16(m, o, &ld.o_w));
+    guard(dev_f32(m, lw.o_b, d, &ld.o_b));
+    guard(dev_bf16(m, std::vector<float>(lw.fc1_w, lw.fc1_w + (size_t)f * d), &ld.fc1_w));
+    guard(dev_f32(m, lw.fc1_b, f, &ld.fc1_b));
+    guard(dev_bf16(m, std::vector<float>(lw.fc2_w, lw.fc2_w + (size_t)d * f), &ld.fc2_w));
+    guard(dev_f32(m, lw.fc2_b, d, &ld.fc2_b));
+  }
+  if (rc != GWW_OK) {
+    gww_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return GWW_OK;
+}
+
+extern "C" int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* h) {
+  if (!m || !h) return fail(GWW_ERR_INVALID, "set_head: null argument");
+  if (h->n_layers < 1 || h->n_layers > kHeadMaxLayers)
+    return fail(GWW_ERR_INVALID, "set_head: n_layers=%d out of range", h->n_layers);
+  HeadParams hp{};
+  hp.n_layers = h->n_layers;
+  hp.softmax = h->softmax;
+  for (int i = 0; i <= h->n_layers; ++i) {
+    if (h->dims[i] < 1 || h->dims[i] > kHeadMaxWidth)
+      return fail(GWW_ERR_INVALID, "set_head: layer width %d out of range", h->dims[i]);
+    hp.dims[i] = h->dims[i];
+  }
+  for (int i = 0; i < h->n_layers; ++i) {
+    float *dw, *db;
+    GWW_TRY(dev_f32(m, h->w[i], (size_t)h->dims[i] * h->dims[i + 1], &dw));
+    GWW_TRY(dev_f32(m, h->b[i], h->dims[i + 1], &db));
+    hp.w[i] = dw;
+    hp.b[i] = db;
+  }
+  CU_TRY(cudaFuncSetAttribute(head_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              2 * kHeadWPB * kHeadMaxWidth * 4));
+  m->head = hp;
+  m->has_head = true;
+  return GWW_OK;
+}
+
+extern "C" void gww_model_destroy(gww_model_t* m) {
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  delete m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+  __nv_bfloat16* feats_tm;  // [chunk, 3002, 80]
+  float* x;                 // [chunk*1500, d]  residual stream
+  __nv_bfloat16* h;         // [chunk*1500, d]  LN output / attention output
+  __nv_bfloat16* g;         // [chunk*1500, ffn] fc1 output; aliases qkv [.,3d] and conv1 out [chunk,3001,d]
+  float* pooled;            // [chunk, d]
+  float* head_out;          // [chunk, 64]
+  float* gather;            // [chunk, 2048] contiguous strain windows
+  size_t total;
+};
+static size_t align_up(size_t v) { return (v + 1023) & ~(size_t)1023; }
+static Workspace carve(const gww_model* m, int chunk, uint8_t* base) {
+  const size_t d = m->cfg.d_model, f = m->cfg.ffn_dim, M = (size_t)chunk * GWW_N_CTX;
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base + o; };
+  w.feats_tm = (__nv_bfloat16*)take((size_t)chunk * 3002 * 80 * 2);
+  w.x = (float*)take(M * d * 4);
+  w.h = (__nv_bfloat16*)take(M * d * 2);
+  size_t gbytes = M * f * 2;
+  const size_t h1bytes = ((size_t)chunk * 3001 + 2) * d * 2;
+  if (h1bytes > gbytes) gbytes = h1bytes;
+  if (M * 3 * d * 2 > gbytes) gbytes = M * 3 * d * 2;
+  if (M * d * 4 > gbytes) gbytes = M * d * 4;
+  w.g = (__nv_bfloat16*)take(gbytes);
+  w.pooled = (float*)take((size_t)chunk * d * 4);
+  w.head_out = (float*)take((size_t)chunk * 64 * 4);
+  w.gather = (float*)take((size_t)chunk * 2048 * 4);
+  w.total = off;
+  return w;
+}
+extern "C" size_t gww_workspace_bytes(const gww_model_t* m, int chunk) {
+  if (!m || chunk <= 0) return 0;
+  return carve(m, chunk, nullptr).total + 1024;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder on one chunk whose time-major bf16 features are already in ws.feats_tm
+// ------------------------------------------------------------------------------------------------
+static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float* last_hidden,
+                         float* pooled, int use_last_token, cudaStream_t stream) {
+  const int d = m->cfg.d_model, f = m->cfg.ffn_dim;
+  const long M = (long)nc * GWW_N_CTX;
+  const int bn_d = pick_block_n(d), bn_3d = pick_block_n(3 * d), bn_f = pick_block_n(f);
+  __nv_bfloat16* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
+  CU_TRY(cudaMemset2DAsync(h1, (size_t)3001 * d * 2, 0, (size_t)d * 2, nc, stream));
+  {  // conv1 (k=3, pad=1) + GELU : feats_tm [nc,3002,80] -> h1[:,1:,:]
+    GemmCall g{};
+    g.a_base = ws.feats_tm;
+    g.a_dims[0] = 80; g.a_dims[1] = 1; g.a_dims[2] = 3002; g.a_dims[3] = nc;
+    g.a_strides[0] = 160; g.a_strides[1] = 160; g.a_strides[2] = 3002ull * 160;
+    g.w_base = m->conv1_w; g.ktot = 384;
+    g.c_base = h1 + d;
+    g.c_strides[0] = (uint64_t)d * 2; g.c_strides[1] = 3001ull * d * 2;
+    g.p.rows = 3000; g.p.batch = nc; g.p.n = d; g.p.kb_per_tap = 2; g.p.taps = 3; g.p.p_mod = 1;
+    g.p.bias = m->conv1_b; g.p.resid = nullptr; g.p.pos = nullptr;
+    g.epi = EPI_BIAS_GELU_BF16; g.block_n = bn_d;
+    GWW_TRY(run_gemm(g, stream));
+  }
+  {  // conv2 (k=3, stride 2, pad=1) + GELU + embed_positions : h1 -> x [nc,1500,d] f32
+    GemmCall g{};
+    g.a_base = h1;
+    g.a_dims[0] = d; g.a_dims[1] = 2; g.a_dims[2] = 1501; g.a_dims[3] = nc;
+    g.a_strides[0] = (uint64_t)d * 2; g.a_strides[1] = (uint64_t)d * 4; g.a_strides[2] = 3001ull * d * 2;
+    g.w_base = m->conv2_w; g.ktot = 3 * d;
+    g.c_base = ws.x;
+    g.c_strides[0] = (uint64_t)d * 4; g.c_strides[1] = (uint64_t)GWW_N_CTX * d * 4;
+    g.p.rows = GWW_N_CTX; g.p.batch = nc; g.p.n = d; g.p.kb_per_tap = d / 64; g.p.taps = 3; g.p.p_mod = 2;
+    g.p.bias = m->conv2_b; g.p.resid = nullptr; g.p.pos = m->pos_emb;
+    g.epi = EPI_BIAS_GELU_POS_F32; g.block_n = bn_d;
+    GWW_TRY(run_gemm(g, stream));
+  }
+  __nv_bfloat16* qkv = ws.g;
+  for (const LayerDev& ld : m->layers) {
+    GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
+    GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream));
+    GWW_TRY(run_attention(qkv, ws.h, nc, GWW_N_CTX, d, stream));
+    GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_d, stream));
+    GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln2_g, ld.ln2_b, M, d, 0, 1, stream));
+    GWW_TRY(run_linear(ws.h, ld.fc1_w, ws.g, ld.fc1_b, nullptr, M, f, d, EPI_BIAS_GELU_BF16, bn_f, stream));
+    GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x, ld.fc2_b, ws.x, M, d, f, EPI_BIAS_RESID_F32, bn_d, stream));
+  }
+  if (last_hidden != nullptr)
+    GWW_TRY(run_ln_t<float>(ws.x, last_hidden, m->lnp_g, m->lnp_b, M, d, 0, 1, stream));
+  if (pooled != nullptr) {
+    if (use_last_token) {
+      GWW_TRY(run_ln_t<float>(ws.x, pooled, m->lnp_g, m->lnp_b, nc, d, GWW_N_CTX - 1, GWW_N_CTX, stream));
+    } else {
+      float* full = last_hidden;
+      if (full == nullptr) {
+        full = reinterpret_cast<float*>(ws.g);
+        GWW_TRY(run_ln_t<float>(ws.x, full, m->lnp_g, m->lnp_b, M, d, 0, 1, stream));
+      }
+      mean_pool_kernel<0><<<nc, 256, 0, stream>>>(full, pooled, GWW_N_CTX, d);
+      LAUNCH_CHECK();
+    }
+  }
+  return GWW_OK;
+}
+
+static int check_ws(const gww_model* m, int chunk, void* workspace, size_t bytes, Workspace* ws) {
+  if (!m) return fail(GWW_ERR_INVALID, "null model");
+  if (chunk <= 0 || chunk > 32768) return fail(GWW_ERR_INVALID, "chunk=%d out of range", chunk);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  *ws = carve(m, chunk, base);
+  const size_t need = ws->total + (size_t)(base - reinterpret_cast<uint8_t*>(workspace));
+  if (workspace == nullptr || bytes < need)
+    return fail(GWW_ERR_WORKSPACE, "workspace too small: have %zu need %zu bytes", bytes, need);
+  return GWW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int gww_logmel_frontend(const float* strain, long n, float* feats, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !feats || n < 0) return fail(GWW_ERR_INVALID, "logmel_frontend: bad argument");
+  if (n == 0) return GWW_OK;
+  return run_logmel(strain, n, feats, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int gww_encoder_forward(const gww_model_t* m, const float* feats, long n, float* last_hidden,
+                                   float* pooled, int use_last_token, void* workspace,
+                                   size_t workspace_bytes, int chunk, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!feats || n < 0 || (!last_hidden && !pooled)) return fail(GWW_ERR_INVALID, "encoder_forward: bad argument");
+  Workspace ws;
+  GWW_TRY(check_ws(m, chunk, workspace, workspace_bytes, &ws));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = m->cfg.d_model;
+  for (long c0 = 0; c0 < n; c0 += chunk) {
+    const int nc = (int)((n - c0 < chunk) ? n - c0 : chunk);
+    dim3 grid(47, nc);
+    feats_to_timemajor_kernel<<<grid, 256, 0, s>>>(feats + c0 * 80L * 3000L, ws.feats_tm);
+    LAUNCH_CHECK();
+    GWW_TRY(encoder_chunk(m, ws, nc, last_hidden ? last_hidden + c0 * (long)GWW_N_CTX * d : nullptr,
+                          pooled ? pooled + c0 * d : nullptr, use_last_token, s));
+  }
+  return GWW_OK;
+}
+
+static int run_head(const gww_model* m, const float* reps, long B, float* out, cudaStream_t s) {
+  if (!m->has_head) return fail(GWW_ERR_INVALID, "head_forward: no head set on this model");
+  if (B == 0) return GWW_OK;
+  HeadParams hp = m->head;
+  hp.B = (int)B;
+  const unsigned grid = (unsigned)((B + kHeadWPB - 1) / kHeadWPB);
+  head_mlp_kernel<<<grid, 512, 2 * kHeadWPB * kHeadMaxWidth * 4, s>>>(reps, out, hp);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+extern "C" int gww_head_forward(const gww_model_t* m, const float* reps, long B, float* out, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!m || !reps || !out || B < 0) return fail(GWW_ERR_INVALID, "head_forward: bad argument");
+  return run_head(m, reps, B, out, (cudaStream_t)stream);
+}
+
+// strain windows addressed as strain + b*win_stride + i*det_stride -> out [B, C]
+static int forward_logmel_strided(const gww_model* m, const float* strain, long B, int D,
+                                  long win_stride, long det_stride, bool contiguous, float* out,
+                                  float* pooled_out, const Workspace& ws, int chunk, cudaStream_t s) {
+  if (!m->has_head) return fail(GWW_ERR_INVALID, "forward: no head set on this model");
+  if (m->head.dims[0] != m->cfg.d_model * D)
+    return fail(GWW_ERR_INVALID, "forward: head input width %d != d_model*D = %d", m->head.dims[0],
+                m->cfg.d_model * D);
+  const int wchunk = chunk / D;   // whole windows per chunk
+  if (wchunk < 1) return fail(GWW_ERR_INVALID, "forward: chunk=%d smaller than D=%d", chunk, D);
+  const int C = m->head.dims[m->head.n_layers];
+  const int d = m->cfg.d_model;
+  for (long b0 = 0; b0 < B; b0 += wchunk) {
+    const int nb = (int)((B - b0 < wchunk) ? B - b0 : wchunk);
+    const int nc = nb * D;
+    const float* src;
+    if (contiguous) {
+      src = strain + b0 * win_stride;
+    } else {
+      gather_windows_kernel<<<nc, 256, 0, s>>>(strain + b0 * win_stride, ws.gather, nc, D, win_stride, det_stride);
+      LAUNCH_CHECK();
+      src = ws.gather;
+    }
+    GWW_TRY(run_logmel(src, nc, nullptr, ws.feats_tm, s));
+    GWW_TRY(encoder_chunk(m, ws, nc, nullptr, ws.pooled, 1, s));
+    if (pooled_out)
+      CU_TRY(cudaMemcpyAsync(pooled_out + b0 * D * d, ws.pooled, (size_t)nc * d * 4, cudaMemcpyDeviceToDevice, s));
+    GWW_TRY(run_head(m, ws.pooled, nb, out + b0 * C, s));
+  }
+  return GWW_OK;
+}
+
+extern "C" int gww_forward_windows_logmel(const gww_model_t* m, const float* strain, long B, int D,
+                                          float* out, float* pooled_out, void* workspace,
+                                          size_t workspace_bytes, int chunk, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !out || B < 0 || D < 1) return fail(GWW_ERR_INVALID, "forward_windows: bad argument");
+  Workspace ws;
+  GWW_TRY(check_ws(m, chunk, workspace, workspace_bytes, &ws));
+  return forward_logmel_strided(m, strain, B, D, (long)D * 2048, 2048, true, out, pooled_out, ws, chunk,
+                                (cudaStream_t)stream);
+}
+
+__global__ void take_col0_kernel(const float* __restrict__ out, int C, long n, float* __restrict__ scores) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scores[i] = out[i * C];
+}
+
+extern "C" int gww_threshold_compact(const float* out, int C, long n, float thr, long idx_base,
+                                     long* trig_idx, float* trig_score, int* trig_count, int capacity,
+                                     void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!out || !trig_idx || !trig_score || !trig_count || n < 0 || n > 0x7fffffffL)
+    return fail(GWW_ERR_INVALID, "threshold_compact: bad argument");
+  if (n == 0) return GWW_OK;
+  threshold_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(out, C, (int)n, thr, idx_base, trig_idx,
+                                                                trig_score, trig_count, capacity);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+extern "C" int gww_stream_search_logmel(const gww_model_t* m, const float* strain, int D, long n_samples,
+                                        int hop, long first_window, long n_windows, float thr,
+                                        float* scores, long* trig_idx, float* trig_score,
+                                        int* trig_count, int capacity, void* workspace,
+                                        size_t workspace_bytes, int chunk, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !scores || D < 1 || hop < 1 || n_windows < 0 || first_window < 0)
+    return fail(GWW_ERR_INVALID, "stream_search: bad argument");
+  if (n_samples < 2048 || (first_window + n_windows - 1) * hop + 2048 > n_samples)
+    if (n_windows > 0) return fail(GWW_ERR_INVALID, "stream_search: windows exceed the segment");
+  Workspace ws;
+  GWW_TRY(check_ws(m, chunk, workspace, workspace_bytes, &ws));
+  if (!m->has_head) return fail(GWW_ERR_INVALID, "stream_search: no head set");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = m->head.dims[m->head.n_layers];
+  if (C > 64) return fail(GWW_ERR_INVALID, "stream_search: head has %d outputs (> 64)", C);
+  const int wchunk = chunk / D;
+  if (wchunk < 1) return fail(GWW_ERR_INVALID, "stream_search: chunk smaller than D");
+  for (long k0 = 0; k0 < n_windows; k0 += wchunk) {
+    const int nb = (int)((n_windows - k0 < wchunk) ? n_windows - k0 : wchunk);
+    const float* base = strain + (first_window + k0) * hop;
+    GWW_TRY(forward_logmel_strided(m, base, nb, D, hop, n_samples, false, ws.head_out, nullptr, ws, chunk, s));
+    take_col0_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.head_out, C, nb, scores + k0);
+    LAUNCH_CHECK();
+    if (trig_idx && trig_score && trig_count)
+      GWW_TRY(gww_threshold_compact(ws.head_out, C, nb, thr, first_window + k0, trig_idx, trig_score,
+                                    trig_count, capacity, stream));
+  }
+  return GWW_OK;
+}
+
+// ---- building blocks -------------------------------------------------------------------------------
+extern "C" int gww_gemm_bf16(const void* A, const void* W, void* C, const float* bias, const float* resid,
+                             const float* pos, long M, int N, int K, int epilogue, int block_n,
+                             void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!A || !W || !C || M <= 0) return fail(GWW_ERR_INVALID, "gemm: bad argument");
+  if (epilogue == EPI_BIAS_GELU_POS_F32) {
+    // positional table indexed by the row inside a batch entry: expose as batch=1, rows=M
+    GemmCall g{};
+    g.a_base = A;
+    g.a_dims[0] = K; g.a_dims[1] = 1; g.a_dims[2] = M; g.a_dims[3] = 1;
+    g.a_strides[0] = (uint64_t)K * 2; g.a_strides[1] = (uint64_t)K * 2; g.a_strides[2] = (uint64_t)M * K * 2;
+    g.w_base = W; g.ktot = K; g.c_base = C;
+    g.c_strides[0] = (uint64_t)N * 4; g.c_strides[1] = (uint64_t)M * N * 4;
+    g.p.rows = (int)M; g.p.batch = 1; g.p.n = N; g.p.kb_per_tap = K / 64; g.p.taps = 1; g.p.p_mod = 1;
+    g.p.bias = bias; g.p.resid = nullptr; g.p.pos = pos;
+    g.epi = epilogue; g.block_n = block_n ? block_n : pick_block_n(N);
+    return run_gemm(g, (cudaStream_t)stream);
+  }
+  return run_linear(A, W, C, bias, resid, M, N, K, epilogue, block_n ? block_n : pick_block_n(N),
+                    (cudaStream_t)stream);
+}
+
+extern "C" int gww_attention(const void* qkv, void* out, long n, int T, int d_model, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!qkv || !out || n <= 0) return fail(GWW_ERR_INVALID, "attention: bad argument");
+  return run_attention(qkv, out, n, T, d_model, (cudaStream_t)stream);
+}
+
+extern "C" int gww_layernorm(const float* x, void* out, const float* gamma, const float* beta, long rows,
+                             int d, int out_bf16, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!x || !out || rows <= 0) return fail(GWW_ERR_INVALID, "layernorm: bad argument");
+  if (out_bf16) return run_ln_t<__nv_bfloat16>(x, (__nv_bfloat16*)out, gamma, beta, rows, d, 0, 1, (cudaStream_t)stream);
+  return run_ln_t<float>(x, (float*)out, gamma, beta, rows, d, 0, 1, (cudaStream_t)stream);
+}

@@ -1,0 +1,311 @@
+// Front end A, fused: whitened strain window (2048 samples @ 2048 Hz) -> Whisper log-mel features.
+//
+// Replaces, per det-window, the reference's CPU chain
+//   scipy.signal.resample(x, 16000)            Signal_vs_Noise/utils/preprocess.py:44-51 (f32 store :95)
+//   WhisperFeatureExtractor(audio, 16000)      Signal_vs_Noise/src/dataset.py:20-24
+//     -> HF feature_extraction_whisper.py:104-133: zero-pad to 30 s, reflect-padded STFT(400,160,hann),
+//        |.|^2, 80 slaney mels, log10(max(.,1e-10)), clamp to (max-8), (x+4)/4
+// with one kernel: one CTA per det-window, everything staged in shared memory, f64 arithmetic
+// (B200 has full-rate-class FP64; the 1e-4 parity gate leaves no room for f32 leakage noise in the
+// out-of-band mel bins), one pass of coalesced 16-byte stores for the [80,3000] output.
+//
+// Algorithm (validated in numpy by tests/test_logmel_decomp.py):
+//   1. X = FFT_2048(x)                                   radix-2 Stockham in smem
+//   2. y[125q+r] = sum_k c_k e^{2 pi i k (125q+r)/16000}, |k|<=1024, c_k = X_k/2048 (c_+-1024 halved)
+//        k = 128a+k' :  E_r[k'] = sum_a C[a][k'] e^{2 pi i a r/125}
+//                       d_r[k'] = E_r[k'] e^{2 pi i k' r/16000}
+//                       y[125q+r] = Re IFFT_128(d_r)[q]   (one warp per r)
+//      y is rounded to f32 exactly where the reference stores f32 audio.
+//   3. only frames 0..101 touch non-zero audio: folded 400-point real DFT per frame
+//        X_f[k] = (-1)^k u[200] + sum_{n=1..199} (e[n] cos(2 pi kn/400) - i o[n] sin(2 pi kn/400)),
+//        e/o[n] = w[n] (y~[s+n] +- y~[s+400-n]),  one warp per frame, then sparse mel + log10
+//   4. per-sample max, clamp, affine; frames >= 102 are the per-sample constant.
+// Outputs: f32 mel-major [80,3000] (reference layout) and/or bf16 time-major [3002,80] with zero
+// pad rows (the layout the conv-stem TMA im2col wants).
+#pragma once
+#include "ptx.cuh"
+
+namespace gww {
+
+struct LogmelTables {
+  const double2* tw2048;    // [1024]  e^{-2 pi i j/2048}
+  const double2* tw16000;   // [16000] e^{+2 pi i j/16000}
+  const double2* tw125;     // [125]   e^{+2 pi i j/125}
+  const double2* tw400;     // [400]   (cos, sin)(2 pi j/400)
+  const int* mel_lo;        // [80] first FFT bin with non-zero weight
+  const int* mel_cnt;       // [80] number of non-zero weights
+  const int* mel_off;       // [80] offset into mel_w
+  const double* mel_w;      // packed non-zero weights
+};
+
+constexpr int kLmThreads = 512;
+constexpr int kLmWarps = kLmThreads / 32;
+constexpr int kLmLive = 102;
+constexpr int kLmSmemY = 16000 * 4;
+constexpr int kLmSmemC = 17 * 128 * 16;
+constexpr int kLmSmemScratch = 90112;
+constexpr int kLmSmemTw400 = 400 * 16;
+constexpr int kLmSmemTw125 = 125 * 16;
+constexpr int kLmSmemBytes = kLmSmemY + kLmSmemC + kLmSmemScratch + kLmSmemTw400 + kLmSmemTw125 + 128;
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__global__ void __launch_bounds__(kLmThreads, 1)
+logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict__ out_f32,
+              __nv_bfloat16* __restrict__ out_tm, const LogmelTables tb) {
+  extern __shared__ __align__(16) uint8_t lm_smem[];
+  float* y = reinterpret_cast<float*>(lm_smem);
+  double2* Cm = reinterpret_cast<double2*>(lm_smem + kLmSmemY);
+  uint8_t* scratch = lm_smem + kLmSmemY + kLmSmemC;
+  double2* tw400 = reinterpret_cast<double2*>(scratch + kLmSmemScratch);
+  double2* tw125 = tw400 + 400;
+  float* red = reinterpret_cast<float*>(tw125 + 125);
+  float* melout = reinterpret_cast<float*>(Cm);  // phase 3/4 alias: [102][80]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 400; i += kLmThreads) tw400[i] = tb.tw400[i];
+  for (int i = tid; i < 125; i += kLmThreads) tw125[i] = tb.tw125[i];
+
+  for (long w = blockIdx.x; w < n_detwin; w += gridDim.x) {
+    __syncthreads();
+    // ---------------- phase 1: FFT-2048 (Stockham radix-2 DIF, ping-pong in scratch)
+    double2* fa = reinterpret_cast<double2*>(scratch);
+    double2* fb = fa + 2048;
+    const float* xin = strain + w * 2048;
+    for (int i = tid; i < 2048; i += kLmThreads) fa[i] = make_double2(static_cast<double>(xin[i]), 0.0);
+    __syncthreads();
+    {
+      int n = 2048, s = 1;
+#pragma unroll 1
+      for (int st = 0; st < 11; ++st) {
+        const int m = n >> 1;
+        for (int t = tid; t < 1024; t += kLmThreads) {
+          const int pidx = t / s, q = t - pidx * s;
+          const double2 wp = tb.tw2048[pidx * s];
+          const double2 u = fa[q + s * pidx], v = fa[q + s * (pidx + m)];
+          fb[q + s * (2 * pidx)] = make_double2(u.x + v.x, u.y + v.y);
+          fb[q + s * (2 * pidx + 1)] = cmul(make_double2(u.x - v.x, u.y - v.y), wp);
+        }
+        __syncthreads();
+        double2* t2 = fa; fa = fb; fb = t2;
+        n >>= 1; s <<= 1;
+      }
+    }
+    // fa now holds X[0..2047]
+    // ---------------- phase 2a: C[a+8][k'] = c_{128a+k'}
+    for (int i = tid; i < 17 * 128; i += kLmThreads) {
+      const int a = i / 128 - 8, kp = i & 127;
+      const int k = 128 * a + kp;
+      double2 c = make_double2(0.0, 0.0);
+      if (k >= -1024 && k <= 1024) {
+        const double2 X = fa[k >= 0 ? k : -k];
+        const double sc = ((k == 1024 || k == -1024) ? 0.5 : 1.0) / 2048.0;
+        c = make_double2(X.x * sc, (k >= 0 ? X.y : -X.y) * sc);
+      }
+      Cm[i] = c;
+    }
+    __syncthreads();
+    // ---------------- phase 2b: polyphase inverse, one warp per residue r (mod 125)
+    {
+      double2* b0 = reinterpret_cast<double2*>(scratch) + warp * 256;
+      double2* b1 = b0 + 128;
+      for (int r = warp; r < 125; r += kLmWarps) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int kp = lane + 32 * kk;
+          double ex = 0.0, ey = 0.0;
+#pragma unroll
+          for (int a = -8; a <= 8; ++a) {
+            int j = (a * r) % 125;
+            if (j < 0) j += 125;
+            const double2 t = tw125[j];
+            const double2 c = Cm[(a + 8) * 128 + kp];
+            ex += c.x * t.x - c.y * t.y;
+            ey += c.x * t.y + c.y * t.x;
+          }
+          b0[kp] = cmul(make_double2(ex, ey), tb.tw16000[kp * r]);
+        }
+        __syncwarp();
+        double2* pa = b0;
+        double2* pb = b1;
+        int n = 128, s = 1;
+#pragma unroll 1
+        for (int st = 0; st < 7; ++st) {
+          const int m = n >> 1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int t = lane + 32 * h;
+            const int pidx = t / s, q = t - pidx * s;
+            const double2 tw = tb.tw2048[pidx * s * 16];
+            const double2 wp = make_double2(tw.x, -tw.y);  // conj -> e^{+2 pi i p/n}
+            const double2 u = pa[q + s * pidx], v = pa[q + s * (pidx + m)];
+            pb[q + s * (2 * pidx)] = make_double2(u.x + v.x, u.y + v.y);
+            pb[q + s * (2 * pidx + 1)] = cmul(make_double2(u.x - v.x, u.y - v.y), wp);
+          }
+          __syncwarp();
+          double2* t2 = pa; pa = pb; pb = t2;
+          n >>= 1; s <<= 1;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int q = lane + 32 * kk;
+          y[125 * q + r] = static_cast<float>(pa[q].x);   // f32 audio, as the reference stores it
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 3: live frames, one warp per frame
+    float lmax = -10.0f;
+    {
+      double* eo = reinterpret_cast<double*>(scratch) + warp * 608;  // e[200] | o[200] | pw[208]
+      double* ev = eo;
+      double* ov = eo + 200;
+      double* pw = eo + 400;
+      for (int f = warp; f < kLmLive; f += kLmWarps) {
+        const int base = 160 * f - 200;
+        double u200;
+        {
+          const int i200 = base + 200;
+          u200 = (i200 < 16000) ? static_cast<double>(y[i200]) : 0.0;   // w[200] = 1, i200 >= 0
+        }
+        for (int nn = lane; nn < 200; nn += 32) {
+          if (nn >= 1) {
+            const int ia = base + nn, ib = base + 400 - nn;
+            const double ya = (ia < 0) ? y[-ia] : ((ia < 16000) ? y[ia] : 0.0f);
+            const double yb = (ib < 0) ? y[-ib] : ((ib < 16000) ? y[ib] : 0.0f);
+            const double wn = 0.5 - 0.5 * tw400[nn].x;
+            ev[nn] = wn * (ya + yb);
+            ov[nn] = wn * (ya - yb);
+          }
+        }
+        __syncwarp();
+        double re[7], im[7];
+        int jj[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int k = lane + 32 * i;
+          re[i] = (k & 1) ? -u200 : u200;
+          im[i] = 0.0;
+          jj[i] = 0;
+        }
+#pragma unroll 1
+        for (int nn = 1; nn < 200; ++nn) {
+          const double en = ev[nn], on = ov[nn];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int k = lane + 32 * i;
+            int j = jj[i] + k;
+            if (j >= 400) j -= 400;
+            jj[i] = j;
+            const double2 t = tw400[j];
+            re[i] = fma(en, t.x, re[i]);
+            im[i] = fma(-on, t.y, im[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int k = lane + 32 * i;
+          if (k <= 200) pw[k] = re[i] * re[i] + im[i] * im[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int mm = lane + 32 * i;
+          if (mm < 80) {
+            const int lo = tb.mel_lo[mm], cnt = tb.mel_cnt[mm], off = tb.mel_off[mm];
+            double acc = 0.0;
+            for (int c = 0; c < cnt; ++c) acc = fma(tb.mel_w[off + c], pw[lo + c], acc);
+            const float lv = static_cast<float>(log10(fmax(acc, 1e-10)));
+            melout[f * 80 + mm] = lv;
+            lmax = fmaxf(lmax, lv);
+          }
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if (lane == 0) red[warp] = lmax;
+    __syncthreads();
+    float gmax = red[0];
+#pragma unroll
+    for (int i = 1; i < kLmWarps; ++i) gmax = fmaxf(gmax, red[i]);
+    const float floorv = gmax - 8.0f;
+    const float cconst = (fmaxf(-10.0f, floorv) + 4.0f) * 0.25f;
+    // ---------------- phase 4: outputs
+    if (out_f32 != nullptr) {
+      float4* o4 = reinterpret_cast<float4*>(out_f32 + w * (80L * 3000L));
+      for (int idx = tid; idx < 80 * 750; idx += kLmThreads) {
+        const int mm = idx / 750, c4 = idx - mm * 750;
+        const int t0 = 4 * c4;
+        float4 v = make_float4(cconst, cconst, cconst, cconst);
+        if (t0 < kLmLive) {
+          float tmp[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int t = t0 + e;
+            tmp[e] = (t < kLmLive) ? (fmaxf(melout[t * 80 + mm], floorv) + 4.0f) * 0.25f : cconst;
+          }
+          v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+        o4[idx] = v;
+      }
+    }
+    if (out_tm != nullptr) {
+      uint4* o4 = reinterpret_cast<uint4*>(out_tm + w * (3002L * 80L));
+      const uint32_t cc = pack_bf16x2(cconst, cconst);
+      for (int idx = tid; idx < 3002 * 10; idx += kLmThreads) {
+        const int pr = idx / 10, c = idx - pr * 10;
+        uint4 v = make_uint4(cc, cc, cc, cc);
+        if (pr == 0 || pr == 3001) {
+          v = make_uint4(0u, 0u, 0u, 0u);
+        } else if (pr - 1 < kLmLive) {
+          const float* src = melout + (pr - 1) * 80 + c * 8;
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = (fmaxf(src[2 * e], floorv) + 4.0f) * 0.25f;
+            const float a1 = (fmaxf(src[2 * e + 1], floorv) + 4.0f) * 0.25f;
+            pk[e] = pack_bf16x2(a0, a1);
+          }
+          v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        o4[idx] = v;
+      }
+    }
+  }
+}
+
+// Reference-layout features [n,80,3000] f32 (what HF WhisperEncoder.forward takes,
+// modeling_whisper.py:593-617) -> bf16 time-major zero-padded [n,3002,80] for the conv-stem GEMM.
+__global__ void __launch_bounds__(256)
+feats_to_timemajor_kernel(const float* __restrict__ feats, __nv_bfloat16* __restrict__ out_tm) {
+  __shared__ float tile[80][65];
+  const long w = blockIdx.y;
+  const int t0 = blockIdx.x * 64;              // 47 blocks cover 3000 frames (+ pad rows)
+  const float* src = feats + w * (80L * 3000L);
+  for (int i = threadIdx.x; i < 80 * 64; i += 256) {
+    const int mm = i >> 6, tt = i & 63;
+    tile[mm][tt] = (t0 + tt < 3000) ? src[mm * 3000L + t0 + tt] : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out_tm + w * (3002L * 80L);
+  for (int i = threadIdx.x; i < 64 * 40; i += 256) {
+    const int tt = i / 40, c2 = i - tt * 40;
+    if (t0 + tt < 3000) {
+      reinterpret_cast<uint32_t*>(dst + (t0 + tt + 1) * 80L)[c2] =
+          pack_bf16x2(tile[2 * c2][tt], tile[2 * c2 + 1][tt]);
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < 40; i += 256) {
+      reinterpret_cast<uint32_t*>(dst)[i] = 0u;
+      reinterpret_cast<uint32_t*>(dst + 3001L * 80L)[i] = 0u;
+    }
+  }
+}
+
+}  // namespace gww

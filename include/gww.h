@@ -1,0 +1,166 @@
+/* gww.h -- C ABI of the B200-native GW-Whisper sliding-window inference path.
+ *
+ * Drop-in boundary: the reference has no FFI; its boundary is a set of Python
+ * signatures.  Every entry point below replaces one stage of that Python path and is what a
+ * reference-side binding (ctypes / torch C++ shim) calls.  All pointers marked
+ * "device" are CUDA device pointers on the current device; `stream` is a cudaStream_t passed as
+ * void*.  No entry point allocates device memory on the hot path: callers query
+ * gww_workspace_bytes() and pass a workspace (e.g. from the torch caching allocator).
+ *
+ * Return value: 0 on success, non-zero error code otherwise; gww_last_error() returns a
+ * thread-local human-readable message.  There is NO CPU fallback: on a machine without an sm_100
+ * device every compute entry point fails with GWW_ERR_NO_DEVICE.
+ *
+ * Ordering of det-windows: a batch of B windows with D detectors is laid out [B, D, ...]
+ * (window-major, detector-minor), so pooled representations [B*D, d] reinterpret as the
+ * reference's torch.cat(reps, dim=1) [B, D*d] (MLGWSC-1/inference.py:391).
+ */
+#ifndef GWW_H_
+#define GWW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWW_OK 0
+#define GWW_ERR_INVALID 1
+#define GWW_ERR_CUDA 2
+#define GWW_ERR_NO_DEVICE 3
+#define GWW_ERR_WORKSPACE 4
+
+#define GWW_T_SAMPLES 2048   /* samples per window (1 s @ 2048 Hz)                               */
+#define GWW_N_MELS 80        /* feature rows, HF feature_extraction_whisper.py:70                 */
+#define GWW_N_FRAMES 3000    /* feature columns (30 s / 10 ms), checked at modeling_whisper.py:613 */
+#define GWW_N_CTX 1500       /* encoder tokens after the stride-2 conv                            */
+#define GWW_MAX_HEAD_LAYERS 6
+
+typedef struct gww_model gww_model_t;
+
+/* Whisper encoder geometry (HF configuration_whisper.py): tiny 384/4/6/1536, base 512/6/8/2048,
+ * small 768/12/12/3072.  head_dim must be 64. */
+typedef struct {
+  int d_model;
+  int n_layers;
+  int n_heads;
+  int ffn_dim;
+} gww_encoder_config_t;
+
+/* PEFT-0.12 DoRA adapter of one Linear (reference: Signal_vs_Noise/results/.../adapter_config.json,
+ * r=8, lora_alpha=32, use_dora=true).  All NULL => projection not adapted.  Merged at model creation:
+ *   W' = diag(m / ||W0 + s B A||_row) (W0 + s B A),  s = alpha / r        */
+typedef struct {
+  const float* lora_A;     /* host [r, d_in]  */
+  const float* lora_B;     /* host [d_out, r] */
+  const float* magnitude;  /* host [d_out]    */
+  int r;
+  float scale;             /* alpha / r */
+} gww_dora_t;
+
+/* One WhisperEncoderLayer (HF modeling_whisper.py:361-415).  Host pointers, fp32, nn.Linear layout
+ * [out, in].  k_proj has no bias (:279). */
+typedef struct {
+  const float *ln1_g, *ln1_b;
+  const float *q_w, *q_b, *k_w, *v_w, *v_b, *o_w, *o_b;
+  const float *ln2_g, *ln2_b;
+  const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  gww_dora_t dora_q, dora_k, dora_v, dora_o;
+} gww_layer_weights_t;
+
+typedef struct {
+  const float* conv1_w;   /* host [d, 80, 3]  (modeling_whisper.py:558) */
+  const float* conv1_b;   /* [d] */
+  const float* conv2_w;   /* host [d, d, 3], stride 2 (:559) */
+  const float* conv2_b;   /* [d] */
+  const float* pos_emb;   /* [1500, d] embed_positions (:561) */
+  const float *ln_post_g, *ln_post_b; /* final layer_norm (:643) */
+  const gww_layer_weights_t* layers;  /* [n_layers] */
+} gww_encoder_weights_t;
+
+/* Pooled MLP classifier: Linear+ReLU ... Linear (+Softmax).  Mirrors the nn.Sequential heads at
+ * MLGWSC-1/inference.py:371-382, Signal_vs_Noise/src/model.py:9-20,35-47,
+ * Glitch_classification/src/model.py:10-21 (Dropout is inert in eval). */
+typedef struct {
+  int n_layers;
+  int dims[GWW_MAX_HEAD_LAYERS + 1]; /* dims[0] = d_model * n_detectors */
+  const float* w[GWW_MAX_HEAD_LAYERS]; /* host [dims[i+1], dims[i]] */
+  const float* b[GWW_MAX_HEAD_LAYERS]; /* host [dims[i+1]] */
+  int softmax;                         /* 1 = keep the trailing nn.Softmax(dim=1) */
+} gww_head_weights_t;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+const char* gww_last_error(void);
+const char* gww_version(void);
+/* 0 if the current device is sm_100 and the kernels can run, else GWW_ERR_NO_DEVICE. */
+int gww_device_ok(void);
+
+/* ---- model handle ---------------------------------------------------------------------------- */
+/* Uploads weights, merges DoRA, casts matrices to bf16 (fp32 merge), folds the
+ * head_dim^-0.5 query scale into W_q/b_q.  Immutable afterwards; one in-flight call per workspace. */
+int gww_model_create(const gww_encoder_config_t* cfg, const gww_encoder_weights_t* w,
+                     gww_model_t** out);
+int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* head);
+void gww_model_destroy(gww_model_t* m);
+/* Device bytes needed by forward calls that process up to `chunk` det-windows at a time. */
+size_t gww_workspace_bytes(const gww_model_t* m, int chunk);
+
+/* ---- front end A (replaces scipy.signal.resample + WhisperFeatureExtractor) -------------------- */
+/* strain: device f32 [n, 2048]; feats: device f32 [n, 80, 3000] (reference layout/dtype). */
+int gww_logmel_frontend(const float* strain, long n, float* feats, void* stream);
+
+/* ---- encoder (replaces HF WhisperEncoder.forward with merged DoRA) ----------------------------- */
+/* feats: device f32 [n, 80, 3000].  Exactly one of the outputs may be NULL:
+ *   last_hidden: device f32 [n, 1500, d]  (== encoder(feats).last_hidden_state)
+ *   pooled:      device f32 [n, d]        (== last_hidden_state[:, -1, :] if use_last_token
+ *                                             else .mean(dim=1); inference.py:390) */
+int gww_encoder_forward(const gww_model_t* m, const float* feats, long n, float* last_hidden,
+                        float* pooled, int use_last_token, void* workspace, size_t workspace_bytes,
+                        int chunk, void* stream);
+
+/* ---- head (replaces the nn.Sequential classifier) ---------------------------------------------- */
+/* reps: device f32 [B, dims[0]]; out: device f32 [B, C]. */
+int gww_head_forward(const gww_model_t* m, const float* reps, long B, float* out, void* stream);
+
+/* ---- fused window path: strain -> log-mel -> encoder -> pooled -> head ------------------------- */
+/* strain: device f32 [B, D, 2048]; out: device f32 [B, C].  Equivalent to
+ * two_channel_ligo_binary_classifier.forward / one_channel_... on the log-mel features of each
+ * detector (Signal_vs_Noise/src/model.py:22-29,49-52).  pooled_out (optional, may be NULL):
+ * device f32 [B*D, d]. */
+int gww_forward_windows_logmel(const gww_model_t* m, const float* strain, long B, int D, float* out,
+                               float* pooled_out, void* workspace, size_t workspace_bytes,
+                               int chunk, void* stream);
+
+/* ---- sliding-window search over a resident strain segment -------------------------------------- */
+/* strain: device f32 [D, n_samples] (whitened).  Window k covers samples [k*hop, k*hop+2048)
+ * (SegmentSlicer, MLGWSC-1/inference.py:198-199,254-262).  scores: device f32 [n_windows]
+ * (= out[:, 0], inference.py:481).  Triggers (score > thr, strictly; :484) are appended in window
+ * order to trig_idx/trig_score (device, capacity entries); *trig_count (device int, must be
+ * zeroed by the caller) receives the running count. n_windows = 1 + (n_samples-2048)/hop. */
+int gww_stream_search_logmel(const gww_model_t* m, const float* strain, int D, long n_samples,
+                             int hop, long first_window, long n_windows, float thr, float* scores,
+                             long* trig_idx, float* trig_score, int* trig_count, int capacity,
+                             void* workspace, size_t workspace_bytes, int chunk, void* stream);
+
+/* Ordered threshold compaction on its own (K12): out device f32 [n, C], column 0 is the score. */
+int gww_threshold_compact(const float* out, int C, long n, float thr, long idx_base, long* trig_idx,
+                          float* trig_score, int* trig_count, int capacity, void* stream);
+
+/* ---- building blocks exported for parity tests and profiling ----------------------------------- */
+/* C[M,N] = epilogue(A[M,K] * W[N,K]^T); A, W device bf16 row-major; epilogue ids as in
+ * gemm_tc.cuh (0 bias->bf16, 1 bias+gelu->bf16, 2 bias+resid->f32, 3 bias+gelu+pos->f32). */
+int gww_gemm_bf16(const void* A, const void* W, void* C, const float* bias, const float* resid,
+                  const float* pos, long M, int N, int K, int epilogue, int block_n, void* stream);
+/* qkv device bf16 [n, T, 3d] -> out device bf16 [n, T, d] */
+int gww_attention(const void* qkv, void* out, long n, int T, int d_model, void* stream);
+/* x device f32 [rows, d] -> out bf16 (out_bf16=1) or f32 [rows, d] */
+int gww_layernorm(const float* x, void* out, const float* gamma, const float* beta, long rows, int d,
+                  int out_bf16, void* stream);
+/* number of kernel launches issued by this library in this process (bench.py gpu_launches) */
+long gww_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWW_H_ */

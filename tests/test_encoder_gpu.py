@@ -1,0 +1,123 @@
+"""End-to-end parity of the B200 encoder / model path against the reference's PyTorch path
+(HF WhisperEncoder fp32 + unmerged DoRA + nn.Sequential head) on identical synthetic inputs.
+Gates (BASELINE.json north_star): logits within 2e-2 absolute, and -- because random-init logits
+barely move -- also within 5% of the oracle's own spread for the spread-scaled
+weight set."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _strain(n, D=1, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, D, 2048, generator=g)
+
+
+def _stats(name, got, ref):
+    err = (got - ref).abs()
+    spread = ref.std(0).mean().item() if ref.shape[0] > 1 else float("nan")
+    print(f"{name}: max_abs_err={err.max().item():.4e} mean_abs_err={err.mean().item():.4e} "
+          f"ref_abs_mean={ref.abs().mean().item():.4e} ref_spread(std over batch)={spread:.4e}")
+    return err.max().item(), spread
+
+
+@pytest.mark.parametrize("size,spread", [("tiny", False), ("tiny", True), ("base", True)])
+def test_encoder_last_hidden_state(size, spread):
+    from oracle import encoder as E, logmel as L
+    from gw_whisper_b200 import B200WhisperEncoder
+    dev = torch.device("cuda")
+    ref_enc = E.make_encoder(size, 0, spread=spread)
+    x = _strain(3, 1)[:, 0].numpy()
+    feats = torch.from_numpy(L.logmel_restated(x))
+    with torch.no_grad():
+        ref = ref_enc.to(dev)(feats.to(dev)).last_hidden_state.cpu()
+    enc = B200WhisperEncoder.from_hf(ref_enc.cpu(), chunk=2)     # chunk < n: exercises chunking
+    got = enc(feats.to(dev)).last_hidden_state.cpu()
+    assert got.shape == ref.shape
+    e, _ = _stats(f"last_hidden[{size},spread={spread}]", got, ref)
+    e_last, sp = _stats(f"last_token[{size},spread={spread}]", got[:, -1], ref[:, -1])
+    pooled = enc.pooled(feats.to(dev)).cpu()
+    assert torch.allclose(pooled, got[:, -1], atol=1e-5)
+    mean_pooled = enc.pooled(feats.to(dev), use_last_token=False).cpu()
+    assert torch.allclose(mean_pooled, got.mean(1), atol=1e-4)
+    # LayerNorm'd outputs are O(1): bf16 GEMM inputs bound the error well below 2e-2 relative to scale
+    assert e < 8e-2, "encoder hidden states off"
+    assert e_last < 5e-2
+
+
+def test_encoder_rejects_bad_length():
+    from oracle import encoder as E
+    from gw_whisper_b200 import B200WhisperEncoder
+    enc = B200WhisperEncoder.from_hf(E.make_encoder("tiny", 0), chunk=1)
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 80, 2999, device="cuda"))
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 80, 3000))
+
+
+@pytest.mark.parametrize("spread", [False, True])
+def test_two_channel_model_with_dora(spread):
+    """Signal_vs_Noise two-detector model: reference path = resample + WhisperFeatureExtractor per
+    detector -> PEFT-DoRA encoder (unmerged) -> 4-layer head; ours = fused strain->logits path with
+    DoRA merged at load."""
+    from oracle import encoder as E, logmel as L
+    from gw_whisper_b200 import B200WhisperEncoder, two_channel_ligo_binary_classifier
+    dev = torch.device("cuda")
+    B = 6
+    strain = _strain(B, 2, seed=99)
+    dora = E.synthetic_dora("tiny", targets=("q_proj", "k_proj", "v_proj"))
+    base = E.make_encoder("tiny", 0, spread=spread)
+    enc_b200 = B200WhisperEncoder.from_hf(base, dora=dora, chunk=8)
+    ref_model = E.TwoChannelOracle(E.attach_dora(base, dora), 1)
+    E.seeded_head(ref_model.classifier, seed=3, gain=3.0 if spread else 1.0)
+    feats = torch.from_numpy(L.logmel_restated(strain.numpy()))          # [B,2,80,3000]
+    with torch.no_grad():
+        ref = ref_model.to(dev)(feats[:, 0].to(dev), feats[:, 1].to(dev)).cpu()
+    model = two_channel_ligo_binary_classifier(enc_b200, num_classes=1)
+    model.load_state_dict(ref_model.cpu().state_dict(), strict=False)
+    got_fused = model.forward_strain(strain.to(dev)).cpu()
+    from gw_whisper_b200 import logmel_features
+    f_gpu = logmel_features(strain.to(dev))
+    got_mod = model(f_gpu[:, 0], f_gpu[:, 1]).cpu()
+    e1, sp = _stats(f"two_channel fused logits (spread={spread})", got_fused, ref)
+    e2, _ = _stats(f"two_channel module logits (spread={spread})", got_mod, ref)
+    assert e1 < 2e-2 and e2 < 2e-2
+    if spread:
+        assert sp > 0.05, "spread-scaled weights should give decisive logits"
+        assert e1 < 0.1 * sp + 2e-3
+    # thresholded decisions agree away from a guard band around the threshold
+    thr = ref.median().item()
+    decisive = (ref - thr).abs() > 2e-2
+    assert torch.equal((got_fused > thr)[decisive], (ref > thr)[decisive])
+
+
+def test_glitch_small_multiclass_argmax():
+    from oracle import encoder as E, logmel as L
+    from gw_whisper_b200 import B200WhisperEncoder, glitch_one_channel_classifier, logmel_features
+    dev = torch.device("cuda")
+    B = 4
+    g = torch.Generator().manual_seed(4321)
+    t = torch.arange(2048) / 2048.0
+    strain = torch.randn(B, 1, 2048, generator=g)
+    for i in range(B):   # sine-Gaussian glitches
+        A = 5 + 15 * torch.rand(1, generator=g)
+        f0 = 30 + 470 * torch.rand(1, generator=g)
+        tau = 0.002 + 0.048 * torch.rand(1, generator=g)
+        t0 = 0.3 + 0.4 * torch.rand(1, generator=g)
+        strain[i, 0] += A * torch.exp(-(t - t0) ** 2 / (2 * tau ** 2)) * torch.sin(2 * np.pi * f0 * t)
+    base = E.make_encoder("small", 0, spread=True)
+    ref_model = E.OneChannelOracle(base, head=E.seeded_head(E.head_glitch(768, 11), gain=3.0)).eval()
+    feats = torch.from_numpy(L.logmel_restated(strain[:, 0].numpy()))
+    with torch.no_grad():
+        ref = ref_model.to(dev)(feats.to(dev)).cpu()
+    enc = B200WhisperEncoder.from_hf(base.cpu(), chunk=4)
+    model = glitch_one_channel_classifier(enc, num_classes=11)
+    model.load_state_dict(ref_model.cpu().state_dict(), strict=False)
+    got = model(logmel_features(strain[:, 0].to(dev))).cpu()
+    e, sp = _stats("glitch small logits", got, ref)
+    assert e < 2e-2 or e < 0.1 * sp
+    top2 = ref.topk(2, dim=1).values
+    decisive = (top2[:, 0] - top2[:, 1]) > 4e-2
+    assert torch.equal(got.argmax(1)[decisive], ref.argmax(1)[decisive])
