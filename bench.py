@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: strain-seconds searched per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (N=1): BASELINE.json configs[1] -- "whisper-base encoder log-mel binary classifier, batch
+1024 windows, 1xB200": the Signal_vs_Noise two-detector classifier (whisper-base geometry, random-init
+weights, seeded DoRA adapters on q/k/v merged at load) over 1024 sliding windows x 2 detectors of
+synthetic Gaussian strain per step.  One window advances the search by 204 samples = 0.0996 s of
+strain (MLGWSC-1/inference.py:198-199), so  value = windows * (204/2048) / seconds.
+
+One JSON line on stdout (rank 0).  Under torchrun each rank searches its own time shard (weak
+scaling); the only collective is the all-gather of the small per-rank trigger lists.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HOP = 204
+FS = 2048
+SEC_PER_WINDOW = HOP / FS
+
+
+def flops_per_detwin(d, L, ffn, T=1500):
+    """Algorithmic FLOPs (2*MAC) of the full reference computation per det-window, by GEMM class
+    (tiny 36.938 G, base 87.368 G, small 344.162 G in total)."""
+    conv1 = 2 * 3000 * (80 * 3) * d
+    conv2 = 2 * T * (3 * d) * d
+    qkv = 2 * T * d * 3 * d
+    attn = 4 * T * T * d
+    oproj = 2 * T * d * d
+    fc1 = 2 * T * d * ffn
+    fc2 = 2 * T * ffn * d
+    per = {"gemm_conv1": conv1, "gemm_conv2": conv2, "gemm_qkv": L * qkv, "attention": L * attn,
+           "gemm_out_proj": L * oproj, "gemm_fc1": L * fc1, "gemm_fc2": L * fc2}
+    per["total"] = sum(per.values())
+    return per
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(size: str, chunk: int):
+    """Random-init encoder of the named Whisper geometry + seeded DoRA + seeded 2-detector head.
+    (gw_whisper_b200.synthetic: the same seeded weights the reference arm builds)."""
+    from gw_whisper_b200 import B200WhisperEncoder, two_channel_ligo_binary_classifier
+    from gw_whisper_b200 import synthetic as S
+
+    base = S.make_encoder(size, 0, spread=True)
+    dora = S.synthetic_dora(size, targets=("q_proj", "k_proj", "v_proj"))
+    enc = B200WhisperEncoder.from_hf(base, dora=dora, chunk=chunk)
+    model = two_channel_ligo_binary_classifier(enc, num_classes=1)
+    S.seeded_head(model.classifier, seed=3, gain=3.0)
+    model.refresh()
+    return model, base
+
+
+def reference_windows_per_s(size: str, n_windows: int, threads: int):
+    """The reference's CPU path on `n_windows` two-detector windows: scipy.signal.resample ->
+    WhisperFeatureExtractor (as installed) -> HF WhisperEncoder fp32 with unmerged DoRA -> head."""
+    import numpy as np
+    import torch
+    from oracle import encoder as E, logmel as L
+
+    torch.set_num_threads(threads)
+    base = E.make_encoder(size, 0, spread=True)
+    dora = E.synthetic_dora(size, targets=("q_proj", "k_proj", "v_proj"))
+    model = E.TwoChannelOracle(E.attach_dora(base, dora), 1).eval()
+    E.seeded_head(model.classifier, seed=3, gain=3.0)
+    g = torch.Generator().manual_seed(1234)
+    strain = torch.randn(n_windows, 2, 2048, generator=g).numpy()
+    t0 = time.perf_counter()
+    feats = torch.from_numpy(L.logmel_reference(strain, path="torch"))
+    with torch.no_grad():
+        out = model(feats[:, 0], feats[:, 1])
+    dt = time.perf_counter() - t0
+    return n_windows / dt, dt, float(out.mean())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = args.ref_windows
+    for _ in range(max(args.warmup, 0) and 1):
+        reference_windows_per_s(args.model, 2, threads)
+    times = []
+    for _ in range(args.steps):
+        wps, dt, _ = reference_windows_per_s(args.model, per_step, threads)
+        times.append(dt)
+    tot = sum(times)
+    value = args.steps * per_step * SEC_PER_WINDOW / tot
+    line = {
+        "impl": "reference", "metric": "strain-seconds searched/sec", "value": value,
+        "unit": "strain-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Signal_vs_Noise two-detector classifier, whisper-{args.model} encoder + DoRA(q,k,v) "
+                               f"+ 4-layer head, log-mel front end, 1 s windows @2048 Hz, hop 204",
+                   "windows_per_step": per_step, "detectors": 2},
+        "cpu_baseline": {"value": value, "unit": "strain-s/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step} windows x 2 detectors per step (bounded sample of the 1024-window batch): "
+                                   "scipy resample + HF WhisperFeatureExtractor + HF WhisperEncoder fp32 + unmerged DoRA + head"},
+        "e2e": {"value": value, "unit": "strain-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from gw_whisper_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B, D = args.batch, 2
+    model, base = build_model(args.model, args.chunk)
+    cfg = base.config
+    d, L, ffn = cfg.d_model, cfg.encoder_layers, cfg.encoder_ffn_dim
+
+    # synthetic whitened strain: i.i.d. N(0,1), one shard per rank (seed 1234 + rank)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_strain = torch.randn(B, D, 2048, generator=g).pin_memory()
+    dev_strain = host_strain.to(dev)
+    host_out = torch.empty(B, 1).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    thr = 0.0
+    trig_idx = torch.zeros(B, dtype=torch.long, device=dev)
+    trig_sc = torch.zeros(B, dtype=torch.float32, device=dev)
+    trig_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step_device():
+        flush.zero_()
+        out = model.forward_strain(dev_strain)
+        trig_cnt.zero_()
+        _lib.check(lib.gww_threshold_compact(out.data_ptr(), 1, B, thr, rank * B, trig_idx.data_ptr(),
+                                             trig_sc.data_ptr(), trig_cnt.data_ptr(), B, _lib.stream_ptr()))
+        if world > 1:   # all-gather of the (padded) per-rank trigger lists: the path's only collective
+            cnts = [torch.empty_like(trig_cnt) for _ in range(world)]
+            dist.all_gather(cnts, trig_cnt)
+            scs = [torch.empty_like(trig_sc) for _ in range(world)]
+            dist.all_gather(scs, trig_sc)
+        return out
+
+    def step_e2e():
+        flush.zero_()
+        s = host_strain.to(dev, non_blocking=True)
+        out = model.forward_strain(s)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_out
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.gww_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        timed.launches = lib.gww_launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps, warm)
+    launches_per_run = timed.launches
+    ms_e2e = timed(step_e2e, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # live per-kernel-class timing (CUDA events on the launching stream) over K more steps
+    nk = lib.gww_profile_num_kinds()
+    ms_k = (C.c_double * nk)()
+    cnt_k = (C.c_long * nk)()
+    lib.gww_profile_begin()
+    for _ in range(args.steps):
+        step_device()
+    torch.cuda.synchronize()
+    _lib.check(lib.gww_profile_end(ms_k, cnt_k))
+    names = [lib.gww_profile_kind_name(i).decode() for i in range(nk)]
+    fl = flops_per_detwin(d, L, ffn)
+    n_dw = B * D
+    kernels = {}
+    for i, nm in enumerate(names):
+        if cnt_k[i] == 0:
+            continue
+        ent = {"ms_per_step": ms_k[i] / args.steps, "launches_per_step": cnt_k[i] // args.steps}
+        if nm in fl:
+            ent["tflops"] = fl[nm] * n_dw * args.steps / (ms_k[i] * 1e-3) / 1e12
+        kernels[nm] = ent
+    gemm_names = [n for n in names if n.startswith("gemm_")]
+    gemm_ms = sum(ms_k[names.index(n)] for n in gemm_names)
+    gemm_launches = sum(cnt_k[names.index(n)] for n in gemm_names)
+    gemm_flops = sum(fl[n] for n in gemm_names) * n_dw * args.steps
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_src = "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst)"
+    peak_tf = 1590.0
+    hbm_peak = 6650.0
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", peak_tf)))
+        hbm_peak = float(peaks.get("hbm_gbs", hbm_peak))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all encoder GEMMs)", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": peak_src,
+                "flops_per_launch": gemm_flops / max(gemm_launches, 1),
+                "avg_launch_ms": gemm_ms / max(gemm_launches, 1)}
+    if "logmel" in kernels:
+        lm_bytes = (2048 * 4 + 3002 * 80 * 2) * n_dw   # fused path writes bf16 time-major features
+        kernels["logmel"]["gbs"] = lm_bytes / (kernels["logmel"]["ms_per_step"] * 1e-3) / 1e9
+        kernels["logmel"]["hbm_frac"] = kernels["logmel"]["gbs"] / hbm_peak
+    total_flops = fl["total"] * n_dw
+    value = world * B * SEC_PER_WINDOW * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * B * SEC_PER_WINDOW * args.steps / (ms_e2e * 1e-3)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        wps, dt, _ = reference_windows_per_s(args.model, args.ref_windows, threads)
+        cpu_baseline = {"value": wps * SEC_PER_WINDOW, "unit": "strain-s/s", "cores": threads, "kind": "port",
+                        "sample": f"{args.ref_windows} windows x 2 detectors in {dt:.1f} s: scipy resample + HF "
+                                  "WhisperFeatureExtractor + HF WhisperEncoder fp32 + unmerged DoRA + head"}
+    if rank == 0:
+        line = {
+            "metric": "strain-seconds searched/sec", "value": value, "unit": "strain-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"Signal_vs_Noise two-detector classifier, whisper-{args.model} encoder + DoRA(q,k,v) "
+                                   "+ 4-layer head, log-mel front end, 1 s windows @2048 Hz, hop 204",
+                       "windows_per_step_per_gpu": B, "detectors": D, "det_windows_per_chunk": args.chunk,
+                       "parallelism": f"time-shard dp{world}",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); activations per chunk >> 126 MB L2"},
+            "windows_per_s": world * B * args.steps / (ms_dev * 1e-3),
+            "model_tflops": total_flops * world * args.steps / (ms_dev * 1e-3) / 1e12,
+            "e2e": {"value": e2e_value, "unit": "strain-s/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": host_strain.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
+            "gpu_launches": int(launches_per_run),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="base", choices=["tiny", "base", "small"])
+    ap.add_argument("--batch", type=int, default=1024, help="windows per step per GPU")
+    ap.add_argument("--chunk", type=int, default=256, help="det-windows per encoder pass")
+    ap.add_argument("--ref-windows", type=int, default=8, help="windows per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

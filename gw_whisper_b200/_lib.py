@@ -64,6 +64,10 @@ SYMBOLS = {
     "gww_attention": (_i, [_vp, _vp, _l, _i, _i, _vp]),
     "gww_layernorm": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _vp]),
     "gww_launch_count": (_l, []),
+    "gww_profile_num_kinds": (_i, []),
+    "gww_profile_kind_name": (C.c_char_p, [_i]),
+    "gww_profile_begin": (_i, []),
+    "gww_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -72,6 +72,56 @@ extern "C" int gww_device_ok(void) {
   return GWW_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+// ------------------------------------------------------------------------------------------------
+enum ProfKind : int {
+  PK_LOGMEL = 0, PK_FEATS_TM, PK_GEMM_CONV1, PK_GEMM_CONV2, PK_LN, PK_GEMM_QKV, PK_ATTN, PK_GEMM_O,
+  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_COUNT
+};
+static const char* kProfNames[PK_COUNT] = {"logmel", "feats_to_timemajor", "gemm_conv1", "gemm_conv2",
+                                           "layernorm", "gemm_qkv", "attention", "gemm_out_proj",
+                                           "gemm_fc1", "gemm_fc2", "head", "other"};
+struct ProfRec { cudaEvent_t a, b; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static size_t g_prof_used = 0;
+struct ProfScope {
+  ProfRec* r = nullptr;
+  cudaStream_t s;
+  ProfScope(int kind, cudaStream_t stream) : s(stream) {
+    if (!g_prof_on) return;
+    if (g_prof_used == g_prof_recs.size()) {
+      ProfRec n{};
+      if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
+      g_prof_recs.push_back(n);
+    }
+    r = &g_prof_recs[g_prof_used++];
+    r->kind = kind;
+    cudaEventRecord(r->a, s);
+  }
+  ~ProfScope() { if (r) cudaEventRecord(r->b, s); }
+};
+extern "C" int gww_profile_num_kinds(void) { return PK_COUNT; }
+extern "C" const char* gww_profile_kind_name(int k) { return (k >= 0 && k < PK_COUNT) ? kProfNames[k] : ""; }
+extern "C" int gww_profile_begin(void) { g_prof_used = 0; g_prof_on = true; return GWW_OK; }
+// Stops profiling, waits for the recorded events and accumulates milliseconds / launch counts.
+extern "C" int gww_profile_end(double* ms_by_kind, long* count_by_kind) {
+  g_prof_on = false;
+  for (int k = 0; k < PK_COUNT; ++k) { ms_by_kind[k] = 0.0; count_by_kind[k] = 0; }
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    ProfRec& r = g_prof_recs[i];
+    CU_TRY(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_kind[r.kind] += ms;
+    count_by_kind[r.kind] += 1;
+  }
+  g_prof_used = 0;
+  return GWW_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tensor maps
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +191,7 @@ struct GemmCall {
   GemmParams p;
   int epi;
   int block_n;
+  int kind = PK_OTHER;
 };
 
 template <int BN, int EPI>
@@ -188,6 +239,7 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   const uint64_t cdims[3] = {(uint64_t)g.p.n, (uint64_t)g.p.rows, (uint64_t)g.p.batch};
   const uint32_t cbox[3] = {out_f32 ? 32u : 64u, 32, 1};
   GWW_TRY(make_map(&tmC, out_f32, 3, g.c_base, cdims, g.c_strides, cbox));
+  ProfScope ps(g.kind, stream);
   switch (g.block_n) {
     case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, tmC, g.p, stream);
     case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, tmC, g.p, stream);
@@ -198,8 +250,10 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
 
 // plain Linear: C[M,N] = epi(A[M,K] W[N,K]^T)
 static int run_linear(const void* A, const void* W, void* C, const float* bias, const float* resid,
-                      long M, int N, int K, int epi, int block_n, cudaStream_t stream) {
+                      long M, int N, int K, int epi, int block_n, cudaStream_t stream,
+                      int kind = PK_OTHER) {
   GemmCall g{};
+  g.kind = kind;
   g.a_base = A;
   g.a_dims[0] = K; g.a_dims[1] = 1; g.a_dims[2] = M; g.a_dims[3] = 1;
   g.a_strides[0] = (uint64_t)K * 2; g.a_strides[1] = (uint64_t)K * 2; g.a_strides[2] = (uint64_t)M * K * 2;
@@ -249,6 +303,7 @@ static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaS
     const long nz = (n - z0 < 32768) ? n - z0 : 32768;
     if (z0 != 0) return fail(GWW_ERR_INVALID, "attention: more than 32768 det-windows per call");
     dim3 grid((T + 255) / 256, d / 64, (unsigned)nz);
+    ProfScope ps(PK_ATTN, stream);
     attention_tc_kernel<<<grid, 384, kAttnSmemBytes, stream>>>(tmQ, tmO, ap);
     LAUNCH_CHECK();
   }
@@ -260,6 +315,7 @@ static int run_ln_t(const float* x, OutT* out, const float* g, const float* b, l
                     long in_off, long in_stride, cudaStream_t stream) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const float eps = 1e-5f;
+  ProfScope ps(PK_LN, stream);
   switch (d) {
     case 384: layernorm_kernel<3, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
     case 512: layernorm_kernel<4, OutT><<<grid, 256, 0, stream>>>(x, out, g, b, rows, in_off, in_stride, eps); break;
@@ -355,6 +411,7 @@ static int run_logmel(const float* strain_contig, long n, float* out_f32, __nv_b
                       cudaStream_t stream) {
   GWW_TRY(logmel_tables_init());
   const int grid = (int)(n < (long)g_num_sms ? n : (long)g_num_sms);
+  ProfScope ps(PK_LOGMEL, stream);
   logmel_kernel<<<grid, kLmThreads, kLmSmemBytes, stream>>>(strain_contig, n, out_f32, out_tm, g_lm);
   LAUNCH_CHECK();
   return GWW_OK;
@@ -577,7 +634,7 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     g.c_strides[0] = (uint64_t)d * 2; g.c_strides[1] = 3001ull * d * 2;
     g.p.rows = 3000; g.p.batch = nc; g.p.n = d; g.p.kb_per_tap = 2; g.p.taps = 3; g.p.p_mod = 1;
     g.p.bias = m->conv1_b; g.p.resid = nullptr; g.p.pos = nullptr;
-    g.epi = EPI_BIAS_GELU_BF16; g.block_n = bn_d;
+    g.epi = EPI_BIAS_GELU_BF16; g.block_n = bn_d; g.kind = PK_GEMM_CONV1;
     GWW_TRY(run_gemm(g, stream));
   }
   {  // conv2 (k=3, stride 2, pad=1) + GELU + embed_positions : h1 -> x [nc,1500,d] f32
@@ -590,18 +647,18 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     g.c_strides[0] = (uint64_t)d * 4; g.c_strides[1] = (uint64_t)GWW_N_CTX * d * 4;
     g.p.rows = GWW_N_CTX; g.p.batch = nc; g.p.n = d; g.p.kb_per_tap = d / 64; g.p.taps = 3; g.p.p_mod = 2;
     g.p.bias = m->conv2_b; g.p.resid = nullptr; g.p.pos = m->pos_emb;
-    g.epi = EPI_BIAS_GELU_POS_F32; g.block_n = bn_d;
+    g.epi = EPI_BIAS_GELU_POS_F32; g.block_n = bn_d; g.kind = PK_GEMM_CONV2;
     GWW_TRY(run_gemm(g, stream));
   }
   __nv_bfloat16* qkv = ws.g;
   for (const LayerDev& ld : m->layers) {
     GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
-    GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream));
+    GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
     GWW_TRY(run_attention(qkv, ws.h, nc, GWW_N_CTX, d, stream));
-    GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_d, stream));
+    GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_O));
     GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln2_g, ld.ln2_b, M, d, 0, 1, stream));
-    GWW_TRY(run_linear(ws.h, ld.fc1_w, ws.g, ld.fc1_b, nullptr, M, f, d, EPI_BIAS_GELU_BF16, bn_f, stream));
-    GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x, ld.fc2_b, ws.x, M, d, f, EPI_BIAS_RESID_F32, bn_d, stream));
+    GWW_TRY(run_linear(ws.h, ld.fc1_w, ws.g, ld.fc1_b, nullptr, M, f, d, EPI_BIAS_GELU_BF16, bn_f, stream, PK_GEMM_FC1));
+    GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x, ld.fc2_b, ws.x, M, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2));
   }
   if (last_hidden != nullptr)
     GWW_TRY(run_ln_t<float>(ws.x, last_hidden, m->lnp_g, m->lnp_b, M, d, 0, 1, stream));
@@ -654,7 +711,10 @@ extern "C" int gww_encoder_forward(const gww_model_t* m, const float* feats, lon
   for (long c0 = 0; c0 < n; c0 += chunk) {
     const int nc = (int)((n - c0 < chunk) ? n - c0 : chunk);
     dim3 grid(47, nc);
-    feats_to_timemajor_kernel<<<grid, 256, 0, s>>>(feats + c0 * 80L * 3000L, ws.feats_tm);
+    {
+      ProfScope ps(PK_FEATS_TM, s);
+      feats_to_timemajor_kernel<<<grid, 256, 0, s>>>(feats + c0 * 80L * 3000L, ws.feats_tm);
+    }
     LAUNCH_CHECK();
     GWW_TRY(encoder_chunk(m, ws, nc, last_hidden ? last_hidden + c0 * (long)GWW_N_CTX * d : nullptr,
                           pooled ? pooled + c0 * d : nullptr, use_last_token, s));
@@ -668,6 +728,7 @@ static int run_head(const gww_model* m, const float* reps, long B, float* out, c
   HeadParams hp = m->head;
   hp.B = (int)B;
   const unsigned grid = (unsigned)((B + kHeadWPB - 1) / kHeadWPB);
+  ProfScope ps(PK_HEAD, s);
   head_mlp_kernel<<<grid, 512, 2 * kHeadWPB * kHeadMaxWidth * 4, s>>>(reps, out, hp);
   LAUNCH_CHECK();
   return GWW_OK;

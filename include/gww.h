@@ -159,6 +159,13 @@ int gww_layernorm(const float* x, void* out, const float* gamma, const float* be
                   int out_bf16, void* stream);
 /* number of kernel launches issued by this library in this process (bench.py gpu_launches) */
 long gww_launch_count(void);
+/* Optional per-kernel-class timing: between begin/end every launch is bracketed by CUDA events on
+ * its own stream; end() waits for them and returns total milliseconds and launch counts per class
+ * (arrays of gww_profile_num_kinds() entries).  Used by bench.py for the live roofline numbers. */
+int gww_profile_num_kinds(void);
+const char* gww_profile_kind_name(int kind);
+int gww_profile_begin(void);
+int gww_profile_end(double* ms_by_kind, long* count_by_kind);
 
 #ifdef __cplusplus
 }

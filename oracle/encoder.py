@@ -23,41 +23,8 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-SIZES = {
-    "tiny": dict(d_model=384, encoder_layers=4, encoder_attention_heads=6, encoder_ffn_dim=1536),
-    "base": dict(d_model=512, encoder_layers=6, encoder_attention_heads=8, encoder_ffn_dim=2048),
-    "small": dict(d_model=768, encoder_layers=12, encoder_attention_heads=12, encoder_ffn_dim=3072),
-}
+from gw_whisper_b200.synthetic import SIZES, make_encoder, seeded_head, synthetic_dora  # noqa: F401  (weight factories)
 
-
-def make_encoder(size: str = "tiny", seed: int = 0, init_std: Optional[float] = None,
-                 spread: bool = False) -> nn.Module:
-    """Random-init HF WhisperEncoder (fp32, eval).  `spread=True` rescales the projection / MLP
-    weights and LayerNorm affine so the last-token representation varies O(1) across inputs
-    (default init gives logits with a 1e-4 spread, which makes parity vacuous)."""
-    from transformers import WhisperConfig
-    from transformers.models.whisper.modeling_whisper import WhisperEncoder
-
-    kw = dict(SIZES[size])
-    if init_std is not None:
-        kw["init_std"] = init_std
-    cfg = WhisperConfig(decoder_layers=1, decoder_attention_heads=kw["encoder_attention_heads"],
-                        decoder_ffn_dim=64, **kw)
-    cfg._attn_implementation = "eager"
-    torch.manual_seed(seed)
-    enc = WhisperEncoder(cfg).float().eval()
-    if spread:
-        # probed in this container: (q,k x20; other layer matrices x3; conv x3) lifts the std of the
-        # last-token representation across Gaussian-noise windows from 1.5e-3 to ~0.36
-        with torch.no_grad():
-            for name, p in enc.named_parameters():
-                if name.endswith("q_proj.weight") or name.endswith("k_proj.weight"):
-                    p.mul_(20.0)
-                elif name.startswith("layers.") and name.endswith("weight") and p.dim() == 2:
-                    p.mul_(3.0)
-                elif name.startswith("conv") and name.endswith("weight"):
-                    p.mul_(3.0)
-    return enc
 
 
 class DoraLinear(nn.Module):
@@ -102,24 +69,6 @@ def attach_dora(encoder: nn.Module, dora: Dict[str, object]) -> nn.Module:
                     DoraLinear(lin, torch.as_tensor(t[base + "lora_A.weight"]),
                                torch.as_tensor(t[base + "lora_B.weight"]), torch.as_tensor(m), scale))
     return encoder
-
-
-def synthetic_dora(size: str, seed: int = 7, r: int = 8, alpha: float = 32.0,
-                   targets=("k_proj", "v_proj")) -> Dict[str, object]:
-    """Seeded adapter with the shipped geometry (r=8, alpha=32, use_dora) for any Whisper size:
-    A ~ kaiming-uniform-ish, small random B, m = ||W0||_row * U(0.8, 1.2) is emulated with U(0.3,1.1)
-    (shipped lora_magnitude_vector values span 0.09..1.12)."""
-    d = SIZES[size]["d_model"]
-    L = SIZES[size]["encoder_layers"]
-    g = torch.Generator().manual_seed(seed)
-    t = {}
-    for i in range(L):
-        for proj in targets:
-            base = f"base_model.model.layers.{i}.self_attn.{proj}."
-            t[base + "lora_A.weight"] = ((torch.rand(r, d, generator=g) * 2 - 1) / d ** 0.5).numpy()
-            t[base + "lora_B.weight"] = (0.02 * torch.randn(d, r, generator=g)).numpy()
-            t[base + "lora_magnitude_vector"] = (0.3 + 0.8 * torch.rand(d, generator=g)).numpy()
-    return {"tensors": t, "r": r, "lora_alpha": alpha, "use_dora": True}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -176,14 +125,3 @@ class OneChannelOracle(nn.Module):
         return self.classifier(self.encoder(mel).last_hidden_state[:, -1, :])
 
 
-def seeded_head(head: nn.Sequential, seed: int = 3, gain: float = 1.0) -> nn.Sequential:
-    """Deterministic head weights (default nn.Linear init under a fixed seed, optional gain so the
-    logits have O(1) spread with random-init encoders)."""
-    g = torch.Generator().manual_seed(seed)
-    with torch.no_grad():
-        for m in head:
-            if isinstance(m, nn.Linear):
-                bound = gain / m.in_features ** 0.5
-                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * bound)
-                m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) * bound)
-    return head.eval()
