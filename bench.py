@@ -224,10 +224,12 @@ def run_b200(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.gww_launch_count()
+        h0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        timed.host_issue_ms = (time.perf_counter() - h0) * 1e3 / steps
         torch.cuda.synchronize()
         timed.launches = lib.gww_launch_count() - l0
         ms = e0.elapsed_time(e1)
@@ -244,6 +246,7 @@ def run_b200(args):
         sampler.start()
     ms_dev = timed(step_device, args.steps, warm)
     launches_per_run = timed.launches
+    host_issue_ms = timed.host_issue_ms
     ms_e2e = timed(step_e2e, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -316,7 +319,7 @@ def run_b200(args):
             "model_tflops": total_flops * world * args.steps / (ms_dev * 1e-3) / 1e12,
             "e2e": {"value": e2e_value, "unit": "strain-s/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_strain.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
-            "gpu_launches": int(launches_per_run),
+            "gpu_launches": int(launches_per_run), "host_issue_ms_per_step": host_issue_ms,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -70,10 +70,11 @@ mean_pool_kernel(const float* __restrict__ hs, float* __restrict__ out, int T, i
 
 // ---------------------------------------------------------------------------------------------
 // Pooled classifier head: x [B, in0] f32 -> Linear(+ReLU) x (L-1) -> Linear -> optional softmax.
-// kHeadWPB windows share one CTA so each weight row is read once per 8 windows; a warp owns an
-// output neuron and its lanes stride over the input (coalesced weight reads, shuffle reduce).
+// One launch per Linear so every layer fills the machine: CTA = 8 output neurons x 16 windows,
+// a warp owns one neuron, its lanes stride over the input with float4 loads (coalesced weight rows,
+// conflict-free smem reads of the 16 staged input rows), shuffle reduction, fp32 throughout.
 constexpr int kHeadMaxLayers = 6;
-constexpr int kHeadWPB = 8;
+constexpr int kHeadWin = 16;
 constexpr int kHeadMaxWidth = 1536;
 struct HeadParams {
   int n_layers;
@@ -84,65 +85,69 @@ struct HeadParams {
   int B;
 };
 
-__global__ void __launch_bounds__(512)
-head_mlp_kernel(const float* __restrict__ x, float* __restrict__ out, const HeadParams hp) {
-  extern __shared__ float hbuf[];                 // 2 x kHeadWPB x kHeadMaxWidth
-  float* cur = hbuf;
-  float* nxt = hbuf + kHeadWPB * kHeadMaxWidth;
-  const int w0 = blockIdx.x * kHeadWPB;
-  const int nw = min(kHeadWPB, hp.B - w0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int in0 = hp.dims[0];
-  for (int i = threadIdx.x; i < kHeadWPB * in0; i += blockDim.x) {
-    const int wdx = i / in0, c = i - wdx * in0;
-    cur[wdx * kHeadMaxWidth + c] = (wdx < nw) ? x[static_cast<size_t>(w0 + wdx) * in0 + c] : 0.f;
+__global__ void __launch_bounds__(256)
+head_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                   const float* __restrict__ bias, float* __restrict__ y, int B, int din, int dout,
+                   int relu) {
+  extern __shared__ __align__(16) float xs[];     // [kHeadWin][din]
+  const int b0 = blockIdx.y * kHeadWin;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kHeadWin * din; i += 256) {
+    const int q = i / din, c = i - q * din;
+    xs[i] = (b0 + q < B) ? x[static_cast<size_t>(b0 + q) * din + c] : 0.f;
   }
   __syncthreads();
-  for (int L = 0; L < hp.n_layers; ++L) {
-    const int din = hp.dims[L], dout = hp.dims[L + 1];
-    const bool last = (L == hp.n_layers - 1);
-    for (int j = warp; j < dout; j += nwarps) {
-      const float* wr = hp.w[L] + static_cast<size_t>(j) * din;
-      float acc[kHeadWPB];
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= dout) return;
+  float acc[kHeadWin];
 #pragma unroll
-      for (int q = 0; q < kHeadWPB; ++q) acc[q] = 0.f;
-      for (int i = lane; i < din; i += 32) {
-        const float wv = __ldg(wr + i);
+  for (int q = 0; q < kHeadWin; ++q) acc[q] = 0.f;
+  const float* wr = W + static_cast<size_t>(j) * din;
+  if ((din & 3) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(wr);
+    const float4* x4 = reinterpret_cast<const float4*>(xs);
+    const int n4 = din >> 2;
+    for (int i = lane; i < n4; i += 32) {
+      const float4 wv = __ldg(w4 + i);
 #pragma unroll
-        for (int q = 0; q < kHeadWPB; ++q) acc[q] = fmaf(wv, cur[q * kHeadMaxWidth + i], acc[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < kHeadWPB; ++q) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-      }
-      if (lane == 0) {
-        const float bj = hp.b[L][j];
-#pragma unroll
-        for (int q = 0; q < kHeadWPB; ++q) {
-          float v = acc[q] + bj;
-          if (!last) v = fmaxf(v, 0.f);
-          nxt[q * kHeadMaxWidth + j] = v;
-        }
+      for (int q = 0; q < kHeadWin; ++q) {
+        const float4 xv = x4[q * n4 + i];
+        acc[q] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[q]))));
       }
     }
-    __syncthreads();
-    float* t = cur; cur = nxt; nxt = t;
-  }
-  const int C = hp.dims[hp.n_layers];
-  if (threadIdx.x < nw) {
-    const float* r = cur + threadIdx.x * kHeadMaxWidth;
-    float* o = out + static_cast<size_t>(w0 + threadIdx.x) * C;
-    if (hp.softmax) {
-      float m = -INFINITY;
-      for (int c = 0; c < C; ++c) m = fmaxf(m, r[c]);
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s += expf(r[c] - m);
-      for (int c = 0; c < C; ++c) o[c] = expf(r[c] - m) / s;
-    } else {
-      for (int c = 0; c < C; ++c) o[c] = r[c];
+  } else {
+    for (int i = lane; i < din; i += 32) {
+      const float wv = __ldg(wr + i);
+#pragma unroll
+      for (int q = 0; q < kHeadWin; ++q) acc[q] = fmaf(wv, xs[q * din + i], acc[q]);
     }
   }
+  float mine = 0.f;
+#pragma unroll
+  for (int q = 0; q < kHeadWin; ++q) {
+    float v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == q) mine = v;
+  }
+  if (lane < kHeadWin && b0 + lane < B) {
+    float v = mine + bias[j];
+    if (relu) v = fmaxf(v, 0.f);
+    y[static_cast<size_t>(b0 + lane) * dout + j] = v;
+  }
+}
+
+// nn.Softmax(dim=1) over C (<= 64) outputs, in place or to `out`
+__global__ void __launch_bounds__(256)
+row_softmax_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= B) return;
+  const float* p = in + static_cast<size_t>(r) * C;
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, p[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(p[c] - m);
+  for (int c = 0; c < C; ++c) out[static_cast<size_t>(r) * C + c] = expf(p[c] - m) / s;
 }
 
 // ---------------------------------------------------------------------------------------------

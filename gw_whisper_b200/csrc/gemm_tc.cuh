@@ -63,7 +63,7 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 4 /*warps*/ * 2 /*bufs*/ * 4096;
   static constexpr int kBiasBytes = 256 * 4;
-  static constexpr int kBarBytes = 128;
+  static constexpr int kBarBytes = 192;  // (2*stages+4) mbarriers + tmem ptr, stages <= 6
   // dynamic smem is declared __align__(1024); no slack needed (checked at kernel entry)
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
   // 227 KB opt-in limit minus the 1 KB the compiler reserves statically for the __align__(1024)

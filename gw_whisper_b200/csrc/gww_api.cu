@@ -397,6 +397,12 @@ static int logmel_tables_init() {
   return GWW_OK;
 }
 
+// zero the first `n16` 16-byte words of every row (row pitch `pitch16` words)
+__global__ void zero_rows_kernel(uint4* base, size_t pitch16, int n16) {
+  uint4* row = base + blockIdx.x * pitch16;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) row[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // strain addressing: det-window w = b*D + i reads strain + b*win_stride + i*det_stride
 __global__ void __launch_bounds__(256)
 gather_windows_kernel(const float* __restrict__ strain, float* __restrict__ out, long n_dw, int D,
@@ -433,6 +439,8 @@ struct gww_model {
   std::vector<void*> owned;
   bool has_head = false;
   HeadParams head{};
+  float* head_scratch = nullptr;   // 2 x rows x kHeadMaxWidth ping-pong activations
+  long head_scratch_rows = 0;
 };
 
 static int dev_f32(gww_model* m, const float* h, size_t n, float** out) {
@@ -562,8 +570,8 @@ extern "C" int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* h) {
     hp.w[i] = dw;
     hp.b[i] = db;
   }
-  CU_TRY(cudaFuncSetAttribute(head_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              2 * kHeadWPB * kHeadMaxWidth * 4));
+  CU_TRY(cudaFuncSetAttribute(head_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kHeadWin * kHeadMaxWidth * 4));
   m->head = hp;
   m->has_head = true;
   return GWW_OK;
@@ -572,6 +580,7 @@ extern "C" int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* h) {
 extern "C" void gww_model_destroy(gww_model_t* m) {
   if (!m) return;
   for (void* p : m->owned) cudaFree(p);
+  if (m->head_scratch) cudaFree(m->head_scratch);
   delete m;
 }
 
@@ -585,6 +594,7 @@ struct Workspace {
   __nv_bfloat16* g;         // [chunk*1500, ffn] fc1 output; aliases qkv [.,3d] and conv1 out [chunk,3001,d]
   float* pooled;            // [chunk, d]
   float* head_out;          // [chunk, 64]
+  float* head_scratch;      // [2, chunk, kHeadMaxWidth]
   float* gather;            // [chunk, 2048] contiguous strain windows
   size_t total;
 };
@@ -605,6 +615,7 @@ static Workspace carve(const gww_model* m, int chunk, uint8_t* base) {
   w.g = (__nv_bfloat16*)take(gbytes);
   w.pooled = (float*)take((size_t)chunk * d * 4);
   w.head_out = (float*)take((size_t)chunk * 64 * 4);
+  w.head_scratch = (float*)take((size_t)2 * chunk * kHeadMaxWidth * 4);
   w.gather = (float*)take((size_t)chunk * 2048 * 4);
   w.total = off;
   return w;
@@ -623,7 +634,10 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
   const long M = (long)nc * GWW_N_CTX;
   const int bn_d = pick_block_n(d), bn_3d = pick_block_n(3 * d), bn_f = pick_block_n(f);
   __nv_bfloat16* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
-  CU_TRY(cudaMemset2DAsync(h1, (size_t)3001 * d * 2, 0, (size_t)d * 2, nc, stream));
+  {  // zero pad row (t = -1) of every sample
+    zero_rows_kernel<<<nc, 128, 0, stream>>>(reinterpret_cast<uint4*>(h1), (size_t)3001 * d * 2 / 16, d * 2 / 16);
+    LAUNCH_CHECK();
+  }
   {  // conv1 (k=3, pad=1) + GELU : feats_tm [nc,3002,80] -> h1[:,1:,:]
     GemmCall g{};
     g.a_base = ws.feats_tm;
@@ -722,15 +736,39 @@ extern "C" int gww_encoder_forward(const gww_model_t* m, const float* feats, lon
   return GWW_OK;
 }
 
-static int run_head(const gww_model* m, const float* reps, long B, float* out, cudaStream_t s) {
+static int run_head(const gww_model* m, const float* reps, long B, float* out, cudaStream_t s,
+                    float* scratch = nullptr) {
   if (!m->has_head) return fail(GWW_ERR_INVALID, "head_forward: no head set on this model");
   if (B == 0) return GWW_OK;
-  HeadParams hp = m->head;
-  hp.B = (int)B;
-  const unsigned grid = (unsigned)((B + kHeadWPB - 1) / kHeadWPB);
+  const HeadParams& hp = m->head;
+  if (scratch == nullptr) {   // standalone call: model-owned scratch, grown on demand (not the hot path)
+    gww_model* mm = const_cast<gww_model*>(m);
+    if (mm->head_scratch_rows < B) {
+      CU_TRY(cudaStreamSynchronize(s));
+      if (mm->head_scratch) CU_TRY(cudaFree(mm->head_scratch));
+      CU_TRY(cudaMalloc(&mm->head_scratch, (size_t)2 * B * kHeadMaxWidth * sizeof(float)));
+      mm->head_scratch_rows = B;
+    }
+    scratch = mm->head_scratch;
+  }
+  float* bufs[2] = {scratch, scratch + (size_t)B * kHeadMaxWidth};
+  const float* cur = reps;
+  const int C = hp.dims[hp.n_layers];
   ProfScope ps(PK_HEAD, s);
-  head_mlp_kernel<<<grid, 512, 2 * kHeadWPB * kHeadMaxWidth * 4, s>>>(reps, out, hp);
-  LAUNCH_CHECK();
+  for (int L = 0; L < hp.n_layers; ++L) {
+    const int din = hp.dims[L], dout = hp.dims[L + 1];
+    const bool last = (L == hp.n_layers - 1);
+    float* dst = (last && !hp.softmax) ? out : bufs[L & 1];
+    dim3 grid((dout + 7) / 8, (unsigned)((B + kHeadWin - 1) / kHeadWin));
+    head_linear_kernel<<<grid, 256, (size_t)kHeadWin * din * sizeof(float), s>>>(
+        cur, hp.w[L], hp.b[L], dst, (int)B, din, dout, last ? 0 : 1);
+    LAUNCH_CHECK();
+    cur = dst;
+  }
+  if (hp.softmax) {
+    row_softmax_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(cur, out, (int)B, C);
+    LAUNCH_CHECK();
+  }
   return GWW_OK;
 }
 
@@ -767,7 +805,7 @@ static int forward_logmel_strided(const gww_model* m, const float* strain, long 
     GWW_TRY(encoder_chunk(m, ws, nc, nullptr, ws.pooled, 1, s));
     if (pooled_out)
       CU_TRY(cudaMemcpyAsync(pooled_out + b0 * D * d, ws.pooled, (size_t)nc * d * 4, cudaMemcpyDeviceToDevice, s));
-    GWW_TRY(run_head(m, ws.pooled, nb, out + b0 * C, s));
+    GWW_TRY(run_head(m, ws.pooled, nb, out + b0 * C, s, ws.head_scratch));
   }
   return GWW_OK;
 }

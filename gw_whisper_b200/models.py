@@ -39,7 +39,7 @@ class _B200Classifier(nn.Module):
         self._head_dirty = True
 
     def _sync_head(self):
-        if self._head_dirty or self.encoder._head_key is not id(self):
+        if self._head_dirty or self.encoder._head_key != id(self):
             softmax = any(isinstance(m, nn.Softmax) for m in self.classifier)
             self.encoder.set_head(_linears(self.classifier), softmax=softmax)
             self.encoder._head_key = id(self)

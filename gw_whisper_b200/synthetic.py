@@ -33,12 +33,14 @@ def make_encoder(size: str = "tiny", seed: int = 0, init_std: Optional[float] = 
     torch.manual_seed(seed)
     enc = WhisperEncoder(cfg).float().eval()
     if spread:
-        # probed in this container: (q,k x20; other layer matrices x3; conv x3) lifts the std of the
-        # last-token representation across Gaussian-noise windows from 1.5e-3 to ~0.36
+        # probed in this container: (q,k x6; other layer matrices x3; conv x3) lifts the std of the
+        # last-token representation across Gaussian-noise windows from 1.2e-4 to ~4e-2 while PyTorch's
+        # own bf16 autocast of the same model still agrees with fp32 to ~1e-2 (x20 on q,k gives a 0.4
+        # spread but is chaotic: torch bf16 autocast itself is then off by O(1))
         with torch.no_grad():
             for name, p in enc.named_parameters():
                 if name.endswith("q_proj.weight") or name.endswith("k_proj.weight"):
-                    p.mul_(20.0)
+                    p.mul_(6.0)
                 elif name.startswith("layers.") and name.endswith("weight") and p.dim() == 2:
                     p.mul_(3.0)
                 elif name.startswith("conv") and name.endswith("weight"):

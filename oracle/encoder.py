@@ -33,7 +33,9 @@ class DoraLinear(nn.Module):
     def __init__(self, base: nn.Linear, A: torch.Tensor, B: torch.Tensor, m: torch.Tensor, scale: float):
         super().__init__()
         self.base, self.scale = base, float(scale)
-        self.A, self.B, self.m = A.float(), B.float(), m.float()
+        self.register_buffer("A", A.float().clone())
+        self.register_buffer("B", B.float().clone())
+        self.register_buffer("m", m.float().clone())
 
     def forward(self, x):
         W0 = self.base.weight
