@@ -170,6 +170,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
     const uint32_t tO = tmem_base + lane_off + 384 + t * 64;
     constexpr float kLog2e = 1.4426950408889634f;
     float m_used = 0.f, l = 0.f;
+    if (t == 1) named_bar_arrive(2, 256);   // warpgroup 0 owns the first turn
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(bar_sfull + 8 * t, j & 1);
       tc_fence_after();
@@ -220,6 +221,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
       }
       const float mneg = -m_used * kLog2e;
       float l0 = 0.f, l1 = 0.f;
+      // exp phase: the two softmax warpgroups take turns on the MUFU pipe (named barriers 2/3) so
+      // that one group's exponentials overlap the other group's P.V / next Q.K^T on the tensor pipe
+      named_bar_sync(2 + t, 256);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t pk[32];
@@ -235,6 +239,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
         tmem_st32(tP + h * 32, pk);
       }
       l += l0 + l1;
+      if (t == 0 || j + 1 < nkv) named_bar_arrive(3 - t, 256);   // pass the turn
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_pfull + 8 * t);
