@@ -13,7 +13,18 @@
 //                       MN-major B operand straight from its TMA tile), M=128 N=64 K=128
 // TMEM map (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
 // Warps: WG0/WG1 = softmax for query tile 0/1, WG2 = {w8: TMA producer, w9: MMA issuer + TMEM alloc}.
+//
+// Scheduling (from the r1 ncu source profile: softmax warps spent 1/3 of their time waiting for S):
+//   * S_t(j+1) is issued as soon as softmax t has copied S_t(j) into registers (s_free barrier), not
+//     after P_t(j): the tensor work runs a whole tile ahead of the MUFU-bound softmax chain;
+//   * P_t(j).V(j) is issued when P is ready; softmax only waits for its completion (pv_done) right
+//     before it overwrites P / rescales O for tile j+1;
+//   * the two softmax warpgroups alternate their exponential phases (named barriers 2/3);
+//   * inside a phase FFMA / MUFU.EX2 / (FADD, F2FP) are software-pipelined 32 columns apart so no
+//     instruction waits on a just-issued MUFU; key masking exists only in the last tile's code.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace gww {
@@ -49,7 +60,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
   const uint32_t bar_sfull = bar_vempty + 8 * kAttnStages;  // 2
   const uint32_t bar_pfull = bar_sfull + 16;                // 2
   const uint32_t bar_ofull = bar_pfull + 16;                // 2
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 1 + 4 * kAttnStages + 6);
+  const uint32_t bar_sfree = bar_ofull + 16;                // 2 (softmax -> mma: S copied to registers)
+  const uint32_t bar_pvdone = bar_sfree + 16;               // 2 (mma -> softmax: P.V finished)
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 1 + 4 * kAttnStages + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,6 +85,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
       mbar_init(bar_sfull + 8 * i, 1);
       mbar_init(bar_pfull + 8 * i, 128);
       mbar_init(bar_ofull + 8 * i, 1);
+      mbar_init(bar_sfree + 8 * i, 128);
+      mbar_init(bar_pvdone + 8 * i, 1);
     }
     fence_mbar_init();
   }
@@ -126,38 +141,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
         }
         umma_commit(bar_kempty);
       }
-      int stage = 0;
+      // issue order per step j:  S0(j+1) | P1(j-1).V | S1(j+1) | P0(j).V   (matches the order in
+      // which the staggered softmax groups produce their events; any other order is still safe)
+      auto issue_s = [&](int t, const uint64_t kdesc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
+        umma_commit(bar_sfull + 8 * t);
+      };
+      auto issue_pv = [&](int t, const uint64_t vdesc, bool first) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tO[t], tP[t] + 8 * k, vdesc + 128 * k, kIdescO, (!first || k) ? 1u : 0u);
+        umma_commit(bar_pvdone + 8 * t);
+      };
+      int stage = 0;              // stage of K/V tile j
       uint32_t phase = 0;
+      int pstage = 0;             // stage of V tile j-1
       for (int j = 0; j < nkv; ++j) {
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == kAttnStages) { nstage = 0; nphase ^= 1; }
         const bool has_next = (j + 1 < nkv);
-        mbar_wait(bar_vfull + 8 * stage, phase);
-        if (has_next) mbar_wait(bar_kfull + 8 * nstage, nphase);
-        const uint64_t vdesc = make_sw128_desc(smem_u32(v_s + stage * 16384));
-        const uint64_t kdesc = make_sw128_desc(smem_u32(k_s + nstage * 16384));
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(bar_pfull + 8 * t, j & 1);
+        const uint64_t kdesc_n = make_sw128_desc(smem_u32(k_s + nstage * 16384));
+        if (has_next) {
+          mbar_wait(bar_kfull + 8 * nstage, nphase);
+          mbar_wait(bar_sfree + 8 * 0, j & 1);
           tc_fence_after();
-          // O_t (+)= P_t V_j : 8 K-steps of 16 keys; P advances 8 TMEM columns (16 bf16),
-          // V advances 16 rows x 128 B = 2048 B (=> +128 in the descriptor address field).
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_ts(tO[t], tP[t] + 8 * k, vdesc + 128 * k, kIdescO, (j | k) ? 1u : 0u);
-          if (!has_next) umma_commit(bar_ofull + 8 * t);
-          if (has_next) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
-            umma_commit(bar_sfull + 8 * t);
-          }
+          issue_s(0, kdesc_n);
         }
-        umma_commit(bar_vempty + 8 * stage);
-        if (has_next) umma_commit(bar_kempty + 8 * nstage);
+        if (j >= 1) {
+          mbar_wait(bar_pfull + 8 * 1, (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, make_sw128_desc(smem_u32(v_s + pstage * 16384)), j - 1 == 0);
+          umma_commit(bar_vempty + 8 * pstage);
+        }
+        if (has_next) {
+          mbar_wait(bar_sfree + 8 * 1, j & 1);
+          tc_fence_after();
+          issue_s(1, kdesc_n);
+          umma_commit(bar_kempty + 8 * nstage);
+        }
+        mbar_wait(bar_vfull + 8 * stage, phase);
+        mbar_wait(bar_pfull + 8 * 0, j & 1);
+        tc_fence_after();
+        issue_pv(0, make_sw128_desc(smem_u32(v_s + stage * 16384)), j == 0);
+        if (!has_next) umma_commit(bar_ofull + 8 * 0);
+        pstage = stage;
         stage = nstage;
         phase = nphase;
       }
+      mbar_wait(bar_pfull + 8 * 1, (nkv - 1) & 1);
+      tc_fence_after();
+      issue_pv(1, make_sw128_desc(smem_u32(v_s + pstage * 16384)), nkv - 1 == 0);
+      umma_commit(bar_vempty + 8 * pstage);
+      umma_commit(bar_ofull + 8 * 1);
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -171,8 +208,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
     constexpr float kLog2e = 1.4426950408889634f;
     float m_used = 0.f, l = 0.f;
     if (t == 1) named_bar_arrive(2, 256);   // warpgroup 0 owns the first turn
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(bar_sfull + 8 * t, j & 1);
+    const uint32_t b_sfull = bar_sfull + 8 * t, b_sfree = bar_sfree + 8 * t;
+    const uint32_t b_pfull = bar_pfull + 8 * t, b_pvdone = bar_pvdone + 8 * t;
+
+    auto tile = [&](const int j, auto mask_tag) {
+      constexpr bool kMask = decltype(mask_tag)::value;
+      mbar_wait(b_sfull, j & 1);
       tc_fence_after();
       uint32_t s[4][32];
       tmem_ld32(tS + 0, s[0]);
@@ -180,8 +221,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
       tmem_ld32(tS + 64, s[2]);
       tmem_ld32(tS + 96, s[3]);
       tmem_wait_ld();
-      const int valid = p.T - j * 128;          // keys [0, valid) of this tile exist
-      if (valid < 128) {
+      tc_fence_before();
+      mbar_arrive(b_sfree);                      // S_t is in registers: the next Q.K^T may overwrite it
+      if constexpr (kMask) {
+        const int valid = p.T - j * 128;         // keys [0, valid) of this tile exist
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -204,15 +247,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
         // keeps exp2 arguments <= 8.
         const bool need = (mt - m_used) * kLog2e > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(b_pvdone, (j - 1) & 1);      // O_t must be complete before it is rescaled
+          tc_fence_after();
           const float sc = need ? fast_exp2((m_used - mt) * kLog2e) : 1.0f;
-          uint32_t o[32];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld32(tO + h * 32, o);
+          uint32_t o[16];
+#pragma unroll 1
+          for (int h = 0; h < 4; ++h) {
+            tmem_ld16(tO + h * 16, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
-            tmem_st32(tO + h * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+            tmem_st16(tO + h * 16, o);
           }
           tmem_wait_st();
           l *= sc;
@@ -221,29 +266,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
       }
       const float mneg = -m_used * kLog2e;
       float l0 = 0.f, l1 = 0.f;
-      // exp phase: the two softmax warpgroups take turns on the MUFU pipe (named barriers 2/3) so
-      // that one group's exponentials overlap the other group's P.V / next Q.K^T on the tensor pipe
+      // exp phase: the two softmax warpgroups take turns on the MUFU pipe (named barriers 2/3)
       named_bar_sync(2 + t, 256);
+      // 3-stage software pipeline over 32-column chunks: FFMA(c+1) | EX2(c) | sum+pack(c-1)
+      uint32_t pk[32];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t pk[32];
+      for (int i = 0; i < 32; ++i) s[0][i] = __float_as_uint(fmaf(__uint_as_float(s[0][i]), kLog2e, mneg));
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int c0 = h * 64 + 2 * i;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 >> 5][c0 & 31]), kLog2e, mneg));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[(c0 + 1) >> 5][(c0 + 1) & 31]), kLog2e, mneg));
-          l0 += p0;
-          l1 += p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          if (c < 4) s[c][i] = __float_as_uint(fast_exp2(__uint_as_float(s[c][i])));
+          if (c + 1 < 4)
+            s[c + 1][i] = __float_as_uint(fmaf(__uint_as_float(s[c + 1][i]), kLog2e, mneg));
+          if (c >= 1 && (i & 1)) {
+            const float p0 = __uint_as_float(s[c - 1][i - 1]), p1 = __uint_as_float(s[c - 1][i]);
+            l0 += p0;
+            l1 += p1;
+            pk[((c - 1) & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          }
         }
-        tmem_st32(tP + h * 32, pk);
+        if (c == 2 || c == 4) {                  // 64 columns packed -> 32 TMEM columns of P
+          if (c == 2 && j > 0) {
+            mbar_wait(b_pvdone, (j - 1) & 1);    // P_t(j-1).V finished reading P_t
+            tc_fence_after();
+          }
+          tmem_st32(tP + (c == 2 ? 0 : 32), pk);
+        }
       }
       l += l0 + l1;
       if (t == 0 || j + 1 < nkv) named_bar_arrive(3 - t, 256);   // pass the turn
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(bar_pfull + 8 * t);
-    }
+      mbar_arrive(b_pfull);
+    };
+    for (int j = 0; j + 1 < nkv; ++j) tile(j, std::false_type{});
+    if ((p.T & 127) != 0) tile(nkv - 1, std::true_type{});
+    else tile(nkv - 1, std::false_type{});
     // ---- epilogue: O_t / l -> bf16 -> swizzled staging (the dead Q_t buffer) -> TMA store
     mbar_wait(bar_ofull + 8 * t, 0);
     tc_fence_after();

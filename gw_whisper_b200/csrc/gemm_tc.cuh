@@ -10,8 +10,11 @@
 //   * W is [N, Ktot] bf16, K-major (nn.Linear layout), read through a 2-D map.
 //   * Accumulators live in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps
 //     the MMAs of tile i+1.
-//   * Epilogue warps read TMEM with tcgen05.ld, apply bias / GELU / residual / positional embedding,
-//     stage through 128B-swizzled shared memory and write with TMA stores (clipped at tensor edges).
+//   * Epilogue warps read TMEM with tcgen05.ld (next 32-column chunk prefetched while the current one
+//     is processed), apply bias / GELU / residual / positional embedding and write each thread's row
+//     segment with 256-bit global stores (STG.256: one full 32-byte sector per instruction).  An
+//     earlier version staged through smem + TMA stores; waiting for the TMA unit (shared with the
+//     operand loads) to drain each 4 KB store made every f32-output GEMM epilogue-bound (r1 profile).
 //
 // Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
 // w4..w7 = epilogue (TMEM lane quarter = warp_idx % 4).
@@ -34,6 +37,9 @@ struct GemmParams {
   int kb_per_tap;    // 64-wide K blocks per tap
   int taps;          // 1 (Linear) or 3 (conv k=3)
   int p_mod;         // P: tap -> (tap % P, tap / P) coordinates in dims 1 and 2 of the A map
+  void* c;           // output base (bf16 or f32 depending on the epilogue)
+  long c_row_stride;    // elements between consecutive rows
+  long c_batch_stride;  // elements between batch entries
   const float* bias;   // [n] or nullptr
   const float* resid;  // [batch*rows, n] f32 (EPI_BIAS_RESID_F32)
   const float* pos;    // [rows, n] f32 (EPI_BIAS_GELU_POS_F32)
@@ -54,15 +60,13 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 4 : 6);
+  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 5 : 6);
   static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = 4 /*warps*/ * 2 /*bufs*/ * 4096;
-  static constexpr int kBiasBytes = 256 * 4;
   static constexpr int kBarBytes = 192;  // (2*stages+4) mbarriers + tmem ptr, stages <= 6
   // dynamic smem is declared __align__(1024); no slack needed (checked at kernel entry)
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes;
   // 227 KB opt-in limit minus the 1 KB the compiler reserves statically for the __align__(1024)
   static_assert(kTotal <= 232448 - 1024, "exceeds the dynamic shared memory limit of sm_100");
 };
@@ -70,7 +74,7 @@ struct GemmSmem {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+               const GemmParams p) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   constexpr bool kOutF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
@@ -84,9 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __trap();
   }
   uint8_t* stage_base = smem;
-  uint8_t* staging = smem + kStages * S::kStageBytes;
-  float* bias_s = reinterpret_cast<float*>(staging + S::kStagingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + S::kBiasBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kStages;
@@ -106,7 +108,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -183,13 +184,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;            // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int et = threadIdx.x - 128;   // 0..127
-    uint8_t* my_staging = staging + ew * 8192;
+    constexpr int NC = BN / 32;         // 32-column chunks per tile
     int as = 0;
     uint32_t aphase = 0;
-    int sbuf = 0;
-    int tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_idx = tile / tiles_n;
       const int n_idx = tile - m_idx * tiles_n;
       const int b = m_idx / tiles_per_batch;
@@ -197,126 +195,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = n_idx * BN;
       const int r = r0 + ew * 32 + lane;      // this thread's output row inside the batch entry
       const bool row_ok = r < p.rows;
-
-      // stage this tile's bias slice (single buffer: barrier 2 at the end of the previous tile
-      // guarantees every epilogue warp is done reading it)
-      float* bias_t = bias_s;
-      for (int i = et; i < BN; i += 128) {
-        const int n = n0 + i;
-        bias_t[i] = (p.bias != nullptr && n < p.n) ? __ldg(p.bias + n) : 0.0f;
-      }
-      named_bar_sync(1, 128);
+      const size_t c_off = static_cast<size_t>(b) * p.c_batch_stride +
+                           static_cast<size_t>(row_ok ? r : 0) * p.c_row_stride + n0;
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-
-      if constexpr (!kOutF32) {
-        // bf16 output: 64 columns (128 B per row) per staging buffer
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(t_acc + c * 64, v0);
-          tmem_ld32(t_acc + c * 64 + 32, v1);
-          if (lane == 0) tma_store_wait_read<1>();   // staging[sbuf] no longer being read
-          __syncwarp();
-          tmem_wait_ld();
-          if (c == BN / 64 - 1) {
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);        // accumulator drained -> MMA may reuse it
-          }
-          uint8_t* sb = my_staging + sbuf * 4096 + lane * 128;
-          const float4* bs4 = reinterpret_cast<const float4*>(bias_t + c * 64);
+      uint32_t v[2][32];
+      [[maybe_unused]] uint32_t add[2][32];
+      auto prefetch_add = [&](int c, uint32_t (&dst)[32]) {
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+          const float* rp = p.resid + (static_cast<size_t>(b) * p.rows + (row_ok ? r : 0)) * p.n + n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {              // 8 x 16 B chunks of this row
-            uint32_t pk[4];
-            const float4 bA = bs4[2 * j], bB = bs4[2 * j + 1];
-            const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+          for (int j = 0; j < 4; ++j) {
+            uint32_t t8[8];
+            ld_global_v8(rp + 8 * j, t8);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = j * 8 + e * 2;
-              float a0 = __uint_as_float(col < 32 ? v0[col & 31] : v1[col & 31]);
-              float a1 = __uint_as_float(col < 32 ? v0[(col + 1) & 31] : v1[(col + 1) & 31]);
-              a0 += bv[e * 2];
-              a1 += bv[e * 2 + 1];
-              if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-                a0 = gelu_erf_fast(a0);
-                a1 = gelu_erf_fast(a1);
-              }
-              pk[e] = pack_bf16x2(a0, a1);
-            }
-            *reinterpret_cast<uint4*>(sb + ((j ^ (lane & 7)) << 4)) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int e = 0; e < 8; ++e) dst[8 * j + e] = t8[e];
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmC, smem_u32(my_staging + sbuf * 4096), n0 + c * 64, r0 + ew * 32, b);
-            tma_store_commit();
+        } else if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+          const float* pp = p.pos + static_cast<size_t>(row_ok ? r : 0) * p.n + n0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t t8[8];
+            ld_global_v8(pp + 8 * j, t8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dst[8 * j + e] = t8[e];
           }
-          sbuf ^= 1;
         }
-      } else {
-        // f32 output: 32 columns (128 B per row) per staging buffer
-        const size_t grow = static_cast<size_t>(b) * p.rows + r;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v0[32];
-          tmem_ld32(t_acc + c * 32, v0);
-          float add[32];
-          if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            const float4* rp = reinterpret_cast<const float4*>(p.resid + grow * p.n + n0 + c * 32);
+      };
+      tmem_ld32(t_acc, v[0]);
+      if (n0 < p.n) prefetch_add(0, add[0]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        tmem_wait_ld();
+        if (c + 1 < NC) {
+          tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
+          if (n0 + (c + 1) * 32 < p.n) prefetch_add(c + 1, add[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * as);      // accumulator drained -> MMA may reuse it
+        }
+        const int nc = n0 + c * 32;
+        if (nc < p.n) {                          // (N is a multiple of 64: chunk fully in or out)
+          const uint32_t(&vc)[32] = v[c & 1];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
+          if constexpr (!kOutF32) {
+            uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 t = (row_ok && n0 + c * 32 < p.n) ? rp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-              add[4 * j] = t.x; add[4 * j + 1] = t.y; add[4 * j + 2] = t.z; add[4 * j + 3] = t.w;
+              const float4 bv = (p.bias != nullptr) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float a0 = __uint_as_float(vc[4 * j]) + bv.x, a1 = __uint_as_float(vc[4 * j + 1]) + bv.y;
+              float a2 = __uint_as_float(vc[4 * j + 2]) + bv.z, a3 = __uint_as_float(vc[4 * j + 3]) + bv.w;
+              if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
+                a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
+              }
+              pk[2 * j] = pack_bf16x2(a0, a1);
+              pk[2 * j + 1] = pack_bf16x2(a2, a3);
+            }
+            if (row_ok) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + c * 32;
+              uint32_t lo[8], hi[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { lo[e] = pk[e]; hi[e] = pk[8 + e]; }
+              st_global_v8(dst, lo);
+              st_global_v8(dst + 16, hi);
             }
           } else {
-            const float4* pp = reinterpret_cast<const float4*>(
-                p.pos + static_cast<size_t>(row_ok ? r : 0) * p.n + (n0 + c * 32 < p.n ? n0 + c * 32 : 0));
+            const uint32_t(&ac)[32] = add[c & 1];
+            float* dst = reinterpret_cast<float*>(p.c) + c_off + c * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 t = __ldg(pp + j);
-              add[4 * j] = t.x; add[4 * j + 1] = t.y; add[4 * j + 2] = t.z; add[4 * j + 3] = t.w;
+            for (int j = 0; j < 4; ++j) {
+              uint32_t o[8];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 bv = (p.bias != nullptr) ? __ldg(b4 + 2 * j + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bv.x;
+                float a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bv.y;
+                float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bv.z;
+                float a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bv.w;
+                if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+                  a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
+                  a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
+                }
+                o[4 * h] = __float_as_uint(a0 + __uint_as_float(ac[8 * j + 4 * h]));
+                o[4 * h + 1] = __float_as_uint(a1 + __uint_as_float(ac[8 * j + 4 * h + 1]));
+                o[4 * h + 2] = __float_as_uint(a2 + __uint_as_float(ac[8 * j + 4 * h + 2]));
+                o[4 * h + 3] = __float_as_uint(a3 + __uint_as_float(ac[8 * j + 4 * h + 3]));
+              }
+              if (row_ok) st_global_v8(dst + 8 * j, o);
             }
           }
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          tmem_wait_ld();
-          if (c == BN / 32 - 1) {
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);
-          }
-          uint8_t* sb = my_staging + sbuf * 4096 + lane * 128;
-          const float4* bs4 = reinterpret_cast<const float4*>(bias_t + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float o[4];
-            const float4 bA = bs4[j];
-            const float bv[4] = {bA.x, bA.y, bA.z, bA.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = j * 4 + e;
-              float a = __uint_as_float(v0[col]) + bv[e];
-              if constexpr (EPI == EPI_BIAS_GELU_POS_F32) a = gelu_erf_fast(a);
-              o[e] = a + add[col];
-            }
-            *reinterpret_cast<float4*>(sb + ((j ^ (lane & 7)) << 4)) =
-                make_float4(o[0], o[1], o[2], o[3]);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmC, smem_u32(my_staging + sbuf * 4096), n0 + c * 32, r0 + ew * 32, b);
-            tma_store_commit();
-          }
-          sbuf ^= 1;
         }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
-      named_bar_sync(2, 128);
     }
-    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "attention_tc.cuh"
@@ -142,9 +143,42 @@ static int get_encode() {
   return GWW_OK;
 }
 
+// Encoded tensor maps are cached: the same (buffer, shape) pairs recur every chunk and
+// cuTensorMapEncodeTiled costs tens of microseconds of host time per call.
+struct MapKey {
+  uint64_t v[16];
+  bool operator==(const MapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static std::mutex g_map_mu;
+
 // dims/box are innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).
+static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box);
 static int make_map(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
+  MapKey k{};
+  k.v[0] = (uint64_t)f32 | ((uint64_t)rank << 8);
+  k.v[1] = (uint64_t)(uintptr_t)base;
+  for (int i = 0; i < rank; ++i) { k.v[2 + i] = dims[i]; k.v[11 + i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) k.v[7 + i] = strides_bytes[i];
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_map_cache.find(k);
+  if (it != g_map_cache.end()) { *m = it->second; return GWW_OK; }
+  GWW_TRY(make_map_uncached(m, f32, rank, base, dims, strides_bytes, box));
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache.emplace(k, *m);
+  return GWW_OK;
+}
+static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box) {
   GWW_TRY(get_encode());
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
@@ -195,8 +229,8 @@ struct GemmCall {
 };
 
 template <int BN, int EPI>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                         const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                         cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, EPI>;
   if (!attr_set) {
@@ -206,19 +240,19 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   }
   const int tiles = ((p.rows + 127) / 128) * p.batch * ((p.n + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, 256, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, tmC, p);
+  kern<<<grid, 256, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
   LAUNCH_CHECK();
   return GWW_OK;
 }
 
 template <int BN>
-static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
-                          const GemmParams& p, cudaStream_t s) {
+static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
+                          cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(a, b, c, p, s);
-    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(a, b, c, p, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32>(a, b, c, p, s);
-    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32>(a, b, c, p, s);
+    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(a, b, p, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(a, b, p, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32>(a, b, p, s);
+    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32>(a, b, p, s);
   }
   return fail(GWW_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -229,21 +263,26 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   const bool out_f32 = (g.epi == EPI_BIAS_RESID_F32 || g.epi == EPI_BIAS_GELU_POS_F32);
   if (out_f32 && g.p.n % g.block_n != 0)
     return fail(GWW_ERR_INVALID, "gemm: f32 epilogues need N %% block_n == 0 (N=%d)", g.p.n);
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB;
   const uint32_t abox[4] = {64, 1, 128, 1};
   GWW_TRY(make_map(&tmA, false, 4, g.a_base, g.a_dims, g.a_strides, abox));
   const uint64_t wdims[2] = {(uint64_t)g.ktot, (uint64_t)g.p.n};
   const uint64_t wstr[1] = {(uint64_t)g.ktot * 2};
   const uint32_t wbox[2] = {64, (uint32_t)g.block_n};
   GWW_TRY(make_map(&tmB, false, 2, g.w_base, wdims, wstr, wbox));
-  const uint64_t cdims[3] = {(uint64_t)g.p.n, (uint64_t)g.p.rows, (uint64_t)g.p.batch};
-  const uint32_t cbox[3] = {out_f32 ? 32u : 64u, 32, 1};
-  GWW_TRY(make_map(&tmC, out_f32, 3, g.c_base, cdims, g.c_strides, cbox));
+  GemmParams p = g.p;
+  const uint64_t esz = out_f32 ? 4 : 2;
+  p.c = g.c_base;
+  p.c_row_stride = (long)(g.c_strides[0] / esz);
+  p.c_batch_stride = (long)(g.c_strides[1] / esz);
+  if ((reinterpret_cast<uintptr_t>(g.c_base) & 31) != 0 || (p.c_row_stride * esz) % 32 != 0 ||
+      (p.c_batch_stride * esz) % 32 != 0)
+    return fail(GWW_ERR_INVALID, "gemm: output must be 32-byte aligned (base and strides)");
   ProfScope ps(g.kind, stream);
   switch (g.block_n) {
-    case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, tmC, g.p, stream);
-    case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, tmC, g.p, stream);
-    case 256: return launch_gemm_bn<256>(g.epi, tmA, tmB, tmC, g.p, stream);
+    case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, p, stream);
+    case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, p, stream);
+    case 256: return launch_gemm_bn<256>(g.epi, tmA, tmB, p, stream);
   }
   return fail(GWW_ERR_INVALID, "gemm: block_n must be 128, 192 or 256 (got %d)", g.block_n);
 }
