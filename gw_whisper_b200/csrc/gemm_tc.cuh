@@ -16,8 +16,13 @@
 //     earlier version staged through smem + TMA stores; waiting for the TMA unit (shared with the
 //     operand loads) to drain each 4 KB store made every f32-output GEMM epilogue-bound (r1 profile).
 //
-// Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
-// w4..w7 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (384 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
+// w4..w11 = epilogue (TMEM lane quarter = warp_idx % 4, column half = (warp_idx - 4) / 4).  The
+// encoder's GEMMs have K = 512..3072 against N up to 3072: per output element the tensor pipe needs
+// only K/4096 clocks, so the epilogue (bias, GELU, residual traffic) must sustain ~5-8 outputs per
+// clock per SM.  Two epilogue warps per SM sub-partition hide the TMEM / global-load latencies, and
+// the f32 residual block of each tile is prefetched into L2 by the producer warp
+// (cp.async.bulk.prefetch.tensor) one tile before the epilogue reads it.
 #pragma once
 #include "ptx.cuh"
 
@@ -43,6 +48,7 @@ struct GemmParams {
   const float* bias;   // [n] or nullptr
   const float* resid;  // [batch*rows, n] f32 (EPI_BIAS_RESID_F32)
   const float* pos;    // [rows, n] f32 (EPI_BIAS_GELU_POS_F32)
+  int prefetch_resid;  // tmR is a valid {n, batch*rows} f32 map of resid: L2-prefetch it per tile
 };
 
 // erf-GELU (HF ACT2FN["gelu"], modeling_whisper.py:403) in 8 instructions + 1 MUFU:
@@ -58,6 +64,8 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
   return fmaf(hv, th, hv);
 }
 
+constexpr int kGemmThreads = 384;   // 12 warps: TMA, MMA, TMEM alloc, spare, 8 x epilogue
+
 template <int BN>
 struct GemmSmem {
   static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 5 : 6);
@@ -72,9 +80,9 @@ struct GemmSmem {
 };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   constexpr bool kOutF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
@@ -116,7 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 128);
+      mbar_init(bar_tempty + 8 * i, 256);
     }
     fence_mbar_init();
   }
@@ -139,6 +147,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_idx = tile - m_idx * tiles_n;
         const int b = m_idx / tiles_per_batch;
         const int r0 = (m_idx - b * tiles_per_batch) << 7;
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+          // pull this tile's residual block into L2 one tile ahead of the epilogue that adds it
+          if (p.prefetch_resid) tma_prefetch_l2_2d(&tmR, n_idx * BN, b * p.rows + r0);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t full = bar_full + 8 * stage;
@@ -182,9 +194,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;            // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    constexpr int NC = BN / 32;         // 32-column chunks per tile
+    // ===================== epilogue (8 warps: lane quarter = warp % 4, column half = (warp-4) / 4)
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int half = e >> 2;
+    constexpr int HW = BN / 2;          // accumulator columns handled by one warp
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -192,55 +206,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_idx = tile - m_idx * tiles_n;
       const int b = m_idx / tiles_per_batch;
       const int r0 = (m_idx - b * tiles_per_batch) << 7;
-      const int n0 = n_idx * BN;
-      const int r = r0 + ew * 32 + lane;      // this thread's output row inside the batch entry
+      const int n0 = n_idx * BN + half * HW;
+      const int r = r0 + q * 32 + lane;       // this thread's output row inside the batch entry
       const bool row_ok = r < p.rows;
       const size_t c_off = static_cast<size_t>(b) * p.c_batch_stride +
                            static_cast<size_t>(row_ok ? r : 0) * p.c_row_stride + n0;
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      uint32_t v[2][32];
-      [[maybe_unused]] uint32_t add[2][32];
-      auto prefetch_add = [&](int c, uint32_t (&dst)[32]) {
-        if constexpr (EPI == EPI_BIAS_RESID_F32) {
-          const float* rp = p.resid + (static_cast<size_t>(b) * p.rows + (row_ok ? r : 0)) * p.n + n0 + c * 32;
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * HW;
+      if constexpr (!kOutF32) {
+        constexpr int NC = HW / 32;         // 32-column chunks per warp
+        uint32_t v[2][32];
+        tmem_ld32(t_acc, v[0]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t t8[8];
-            ld_global_v8(rp + 8 * j, t8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dst[8 * j + e] = t8[e];
+        for (int c = 0; c < NC; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < NC) {
+            tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
+          } else {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * as);      // accumulator drained -> MMA may reuse it
           }
-        } else if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-          const float* pp = p.pos + static_cast<size_t>(row_ok ? r : 0) * p.n + n0 + c * 32;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t t8[8];
-            ld_global_v8(pp + 8 * j, t8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dst[8 * j + e] = t8[e];
-          }
-        }
-      };
-      tmem_ld32(t_acc, v[0]);
-      if (n0 < p.n) prefetch_add(0, add[0]);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        tmem_wait_ld();
-        if (c + 1 < NC) {
-          tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
-          if (n0 + (c + 1) * 32 < p.n) prefetch_add(c + 1, add[(c + 1) & 1]);
-        } else {
-          tc_fence_before();
-          mbar_arrive(bar_tempty + 8 * as);      // accumulator drained -> MMA may reuse it
-        }
-        const int nc = n0 + c * 32;
-        if (nc < p.n) {                          // (N is a multiple of 64: chunk fully in or out)
-          const uint32_t(&vc)[32] = v[c & 1];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
-          if constexpr (!kOutF32) {
+          const int nc = n0 + c * 32;
+          if (nc < p.n) {                          // (N is a multiple of 64: chunk fully in or out)
+            const uint32_t(&vc)[32] = v[c & 1];
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -258,34 +249,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + c * 32;
               uint32_t lo[8], hi[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { lo[e] = pk[e]; hi[e] = pk[8 + e]; }
+              for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
               st_global_v8(dst, lo);
               st_global_v8(dst + 16, hi);
             }
+          }
+        }
+      } else {
+        constexpr int NS = HW / 16;         // 16-column steps per warp
+        uint32_t v[2][16];
+        uint32_t add[2][16];
+        const float* addp;                  // residual / positional row segment of this thread
+        if constexpr (EPI == EPI_BIAS_RESID_F32)
+          addp = p.resid + (static_cast<size_t>(b) * p.rows + (row_ok ? r : 0)) * p.n + n0;
+        else
+          addp = p.pos + static_cast<size_t>(row_ok ? r : 0) * p.n + n0;
+        auto load_add = [&](int s, uint32_t (&dst)[16]) {
+          uint32_t t8[8];
+          ld_global_v8(addp + 16 * s, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = t8[i];
+          ld_global_v8(addp + 16 * s + 8, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[8 + i] = t8[i];
+        };
+        tmem_ld16(t_acc, v[0]);
+        load_add(0, add[0]);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          tmem_wait_ld();
+          if (s + 1 < NS) {
+            tmem_ld16(t_acc + (s + 1) * 16, v[(s + 1) & 1]);
+            load_add(s + 1, add[(s + 1) & 1]);
           } else {
-            const uint32_t(&ac)[32] = add[c & 1];
-            float* dst = reinterpret_cast<float*>(p.c) + c_off + c * 32;
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * as);
+          }
+          const uint32_t(&vc)[16] = v[s & 1];
+          const uint32_t(&ac)[16] = add[s & 1];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 16);
+          float* dst = reinterpret_cast<float*>(p.c) + c_off + s * 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t o[8];
+          for (int j = 0; j < 2; ++j) {
+            uint32_t o[8];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float4 bv = (p.bias != nullptr) ? __ldg(b4 + 2 * j + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bv.x;
-                float a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bv.y;
-                float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bv.z;
-                float a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bv.w;
-                if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-                  a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
-                  a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
-                }
-                o[4 * h] = __float_as_uint(a0 + __uint_as_float(ac[8 * j + 4 * h]));
-                o[4 * h + 1] = __float_as_uint(a1 + __uint_as_float(ac[8 * j + 4 * h + 1]));
-                o[4 * h + 2] = __float_as_uint(a2 + __uint_as_float(ac[8 * j + 4 * h + 2]));
-                o[4 * h + 3] = __float_as_uint(a3 + __uint_as_float(ac[8 * j + 4 * h + 3]));
+            for (int h = 0; h < 2; ++h) {
+              const float4 bv = (p.bias != nullptr) ? __ldg(b4 + 2 * j + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bv.x;
+              float a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bv.y;
+              float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bv.z;
+              float a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bv.w;
+              if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+                a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
+                a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
               }
-              if (row_ok) st_global_v8(dst + 8 * j, o);
+              o[4 * h] = __float_as_uint(a0 + __uint_as_float(ac[8 * j + 4 * h]));
+              o[4 * h + 1] = __float_as_uint(a1 + __uint_as_float(ac[8 * j + 4 * h + 1]));
+              o[4 * h + 2] = __float_as_uint(a2 + __uint_as_float(ac[8 * j + 4 * h + 2]));
+              o[4 * h + 3] = __float_as_uint(a3 + __uint_as_float(ac[8 * j + 4 * h + 3]));
             }
+            if (row_ok) st_global_v8(dst + 8 * j, o);
           }
         }
       }

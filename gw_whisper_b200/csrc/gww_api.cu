@@ -161,24 +161,24 @@ static std::mutex g_map_mu;
 
 // dims/box are innermost-first; strides_bytes has rank-1 entries (dim 1..rank-1).
 static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
-                             const uint64_t* strides_bytes, const uint32_t* box);
+                             const uint64_t* strides_bytes, const uint32_t* box, bool swizzle);
 static int make_map(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box) {
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle = true) {
   MapKey k{};
-  k.v[0] = (uint64_t)f32 | ((uint64_t)rank << 8);
+  k.v[0] = (uint64_t)f32 | ((uint64_t)rank << 8) | ((uint64_t)swizzle << 16);
   k.v[1] = (uint64_t)(uintptr_t)base;
   for (int i = 0; i < rank; ++i) { k.v[2 + i] = dims[i]; k.v[11 + i] = box[i]; }
   for (int i = 0; i < rank - 1; ++i) k.v[7 + i] = strides_bytes[i];
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_map_cache.find(k);
   if (it != g_map_cache.end()) { *m = it->second; return GWW_OK; }
-  GWW_TRY(make_map_uncached(m, f32, rank, base, dims, strides_bytes, box));
+  GWW_TRY(make_map_uncached(m, f32, rank, base, dims, strides_bytes, box, swizzle));
   if (g_map_cache.size() > 4096) g_map_cache.clear();
   g_map_cache.emplace(k, *m);
   return GWW_OK;
 }
 static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
-                             const uint64_t* strides_bytes, const uint32_t* box) {
+                             const uint64_t* strides_bytes, const uint32_t* box, bool swizzle) {
   GWW_TRY(get_encode());
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
@@ -190,7 +190,8 @@ static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* bas
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
   CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                         rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(GWW_ERR_CUDA,
@@ -229,8 +230,8 @@ struct GemmCall {
 };
 
 template <int BN, int EPI>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                         cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR,
+                         const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, EPI>;
   if (!attr_set) {
@@ -240,19 +241,19 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   }
   const int tiles = ((p.rows + 127) / 128) * p.batch * ((p.n + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, 256, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, tmR, p);
   LAUNCH_CHECK();
   return GWW_OK;
 }
 
 template <int BN>
-static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
-                          cudaStream_t s) {
+static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& r,
+                          const GemmParams& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(a, b, p, s);
-    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(a, b, p, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32>(a, b, p, s);
-    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32>(a, b, p, s);
+    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(a, b, r, p, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(a, b, r, p, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32>(a, b, r, p, s);
+    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32>(a, b, r, p, s);
   }
   return fail(GWW_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -278,11 +279,20 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(g.c_base) & 31) != 0 || (p.c_row_stride * esz) % 32 != 0 ||
       (p.c_batch_stride * esz) % 32 != 0)
     return fail(GWW_ERR_INVALID, "gemm: output must be 32-byte aligned (base and strides)");
+  CUtensorMap tmR = tmB;   // placeholder unless the residual is prefetched
+  p.prefetch_resid = 0;
+  if (g.epi == EPI_BIAS_RESID_F32 && p.resid != nullptr) {
+    const uint64_t rdims[2] = {(uint64_t)p.n, (uint64_t)p.batch * (uint64_t)p.rows};
+    const uint64_t rstr[1] = {(uint64_t)p.n * 4};
+    const uint32_t rbox[2] = {(uint32_t)g.block_n, 128};
+    GWW_TRY(make_map(&tmR, true, 2, p.resid, rdims, rstr, rbox, false));
+    p.prefetch_resid = 1;
+  }
   ProfScope ps(g.kind, stream);
   switch (g.block_n) {
-    case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, p, stream);
-    case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, p, stream);
-    case 256: return launch_gemm_bn<256>(g.epi, tmA, tmB, p, stream);
+    case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, tmR, p, stream);
+    case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, tmR, p, stream);
+    case 256: return launch_gemm_bn<256>(g.epi, tmA, tmB, tmR, p, stream);
   }
   return fail(GWW_ERR_INVALID, "gemm: block_n must be 128, 192 or 256 (got %d)", g.block_n);
 }
