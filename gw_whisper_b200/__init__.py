@@ -7,8 +7,11 @@ from .models import (  # noqa: F401
     one_channel_ligo_binary_classifier,
     glitch_one_channel_classifier,
 )
+from .qfrontend import (  # noqa: F401
+    QScanB200, QTransformAdapter, GWWhisperClassifier, remove_softmax_from_classifier)
 
 __all__ = [
+    "QScanB200", "QTransformAdapter", "GWWhisperClassifier", "remove_softmax_from_classifier",
     "B200WhisperEncoder", "WhisperGeometry", "load_dora_adapter", "logmel_features",
     "resample_timeseries", "LogMelFeatureExtractor", "two_channel_ligo_binary_classifier",
     "one_channel_ligo_binary_classifier", "glitch_one_channel_classifier",

@@ -44,6 +44,13 @@ class HeadWeights(C.Structure):
                 ("softmax", C.c_int)]
 
 
+class QAdapterWeights(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "conv3_w", "conv3_b",
+                                          "conv4_w", "conv4_b")] + [
+        ("scale", C.c_float), ("bias", C.c_float), ("n_detectors", C.c_int),
+        ("film_gamma", c_float_p), ("film_beta", c_float_p)]
+
+
 # every symbol include/gww.h declares: (restype, argtypes)
 _vp, _l, _i, _f, _sz = C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -60,6 +67,17 @@ SYMBOLS = {
     "gww_forward_windows_logmel": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "gww_stream_search_logmel": (_i, [_vp, _vp, _i, _l, _i, _l, _l, _f, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "gww_threshold_compact": (_i, [_vp, _i, _l, _f, _l, _vp, _vp, _vp, _i, _vp]),
+    "gww_qfront_create": (_i, [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i, _i, C.POINTER(_vp)]),
+    "gww_qfront_set_adapter": (_i, [_vp, C.POINTER(QAdapterWeights)]),
+    "gww_qfront_destroy": (None, [_vp]),
+    "gww_qfront_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "gww_qfront_plan": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gww_qfront_workspace_bytes": (_sz, [_vp, _l]),
+    "gww_qscan": (_i, [_vp, _vp, _l, _l, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gww_qadapter": (_i, [_vp, _vp, _l, _i, _vp, _vp, _sz, _vp]),
+    "gww_forward_windows_qscan": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "gww_stream_search_qscan": (_i, [_vp, _vp, _vp, _i, _l, _i, _l, _l, _i, _f, _vp, _vp, _vp, _vp, _i,
+                                     _vp, _sz, _vp, _sz, _vp]),
     "gww_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _i, _i, _i, _vp]),
     "gww_attention": (_i, [_vp, _vp, _l, _i, _i, _vp]),
     "gww_layernorm": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _vp]),

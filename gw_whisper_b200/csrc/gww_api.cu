@@ -15,6 +15,7 @@
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "logmel.cuh"
+#include "qfront.cuh"
 
 using namespace gww;
 
@@ -79,11 +80,11 @@ extern "C" int gww_device_ok(void) {
 // ------------------------------------------------------------------------------------------------
 enum ProfKind : int {
   PK_LOGMEL = 0, PK_FEATS_TM, PK_GEMM_CONV1, PK_GEMM_CONV2, PK_LN, PK_GEMM_QKV, PK_ATTN, PK_GEMM_O,
-  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_COUNT
+  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_COUNT
 };
 static const char* kProfNames[PK_COUNT] = {"logmel", "feats_to_timemajor", "gemm_conv1", "gemm_conv2",
                                            "layernorm", "gemm_qkv", "attention", "gemm_out_proj",
-                                           "gemm_fc1", "gemm_fc2", "head", "other"};
+                                           "gemm_fc1", "gemm_fc2", "head", "other", "qscan", "qadapter"};
 struct ProfRec { cudaEvent_t a, b; int kind; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof_recs;
@@ -910,6 +911,377 @@ extern "C" int gww_stream_search_logmel(const gww_model_t* m, const float* strai
     const int nb = (int)((n_windows - k0 < wchunk) ? n_windows - k0 : wchunk);
     const float* base = strain + (first_window + k0) * hop;
     GWW_TRY(forward_logmel_strided(m, base, nb, D, hop, n_samples, false, ws.head_out, nullptr, ws, chunk, s));
+    take_col0_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.head_out, C, nb, scores + k0);
+    LAUNCH_CHECK();
+    if (trig_idx && trig_score && trig_count)
+      GWW_TRY(gww_threshold_compact(ws.head_out, C, nb, thr, first_window + k0, trig_idx, trig_score,
+                                    trig_count, capacity, stream));
+  }
+  return GWW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// front end B: Q-transform + Q-Adapter
+// ------------------------------------------------------------------------------------------------
+struct QRowHost {
+  QRow r;
+  double q;
+  float freq;
+};
+struct gww_qfront {
+  int spec_f = 512, spec_t = 512;
+  int n_planes = 0, n_rows = 0, n_tiles = 0;
+  std::vector<double> qs;
+  std::vector<QRowHost> rows;            // plane-major, ascending frequency
+  std::vector<QRow> h_sorted, h_orig;     // host copies of the device plan tables
+  std::vector<float> h_window;
+  QPlan plan{};
+  bool on_device = false;                // tables uploaded (done lazily: the plan itself needs no GPU)
+  bool has_adapter = false;
+  QAdapterDev ad{};
+  int n_detectors = 0;
+  std::vector<void*> owned;
+};
+
+template <typename T>
+static int qf_upload(gww_qfront* qf, const std::vector<T>& h, const T** dptr) {
+  T* d = nullptr;
+  CU_TRY(cudaMalloc(&d, (h.empty() ? 1 : h.size()) * sizeof(T)));
+  qf->owned.push_back(d);
+  if (!h.empty()) CU_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = d;
+  return GWW_OK;
+}
+
+extern "C" void gww_qfront_destroy(gww_qfront_t* qf) {
+  if (!qf) return;
+  for (void* p : qf->owned) cudaFree(p);
+  delete qf;
+}
+
+// Tiling plan of ml4gw QScan / GWpy QTiling (oracle/qscan.py; SURVEY.md section 8a "Q1 tiling plan").
+extern "C" int gww_qfront_create(double duration, double sample_rate, double qmin, double qmax,
+                                 double mismatch, int spec_f, int spec_t, gww_qfront_t** out) {
+  if (!out) return fail(GWW_ERR_INVALID, "qfront_create: null argument");
+  if (duration * sample_rate != 2048.0)
+    return fail(GWW_ERR_INVALID, "qfront_create: only duration*sample_rate == 2048 samples is supported");
+  if (!(qmin > 0 && qmax > qmin) || mismatch <= 0 || spec_t != 512 || spec_f < 16 || spec_f > 512 ||
+      (spec_f % 64) != 0)
+    return fail(GWW_ERR_INVALID, "qfront_create: unsupported parameters (spectrogram must be [64k<=512, 512])");
+  const double PI = 3.14159265358979323846;
+  gww_qfront* qf = new gww_qfront();
+  qf->spec_f = spec_f; qf->spec_t = spec_t;
+  const double deltam = 2.0 * std::sqrt(mismatch / 3.0);
+  const double cumum = std::log(qmax / qmin) / std::sqrt(2.0);
+  const int nplanes = (int)std::fmax(std::ceil(cumum / deltam), 1.0);
+  const double dq = cumum / nplanes;
+  if (nplanes > 8) { delete qf; return fail(GWW_ERR_INVALID, "qfront_create: more than 8 Q planes"); }
+  std::vector<float> window;
+  int eoff = 0;
+  for (int ip = 0; ip < nplanes; ++ip) {
+    const double q = qmin * std::exp(std::sqrt(2.0) * dq * (ip + 0.5));
+    qf->qs.push_back(q);
+    const double qprime = q / std::sqrt(11.0);
+    const double minf = 50.0 * q / (2.0 * PI * duration);
+    const double maxf = sample_rate / 2.0 / (1.0 + 1.0 / qprime);
+    const double fcum = std::log(maxf / minf) * std::sqrt(2.0 + q * q) / 2.0;
+    const int nfreq = (int)std::fmax(1.0, std::ceil(fcum / deltam));
+    const double fstep = fcum / nfreq;
+    const float fstepmin = (float)(1.0 / duration);
+    const double base = std::exp(2.0 / std::sqrt(2.0 + q * q) * fstep);
+    std::vector<float> freqs;
+    for (int i = 0; i < nfreq; ++i) {
+      const float f32 = (float)(minf * std::pow(base, i + 0.5));     // torch.Tensor([...]) is float32
+      const float fl = std::floor(f32 / fstepmin) * fstepmin;
+      if (freqs.empty() || fl != freqs.back()) freqs.push_back(fl);   // ascending input: unique == dedup
+    }
+    for (float f32 : freqs) {
+      const double f = (double)f32;
+      QRowHost rh{};
+      rh.q = q; rh.freq = f32;
+      const int ws = 2 * (int)(f / qprime * duration) + 1;
+      const double tcum = duration * 2.0 * PI * f / q;
+      const int log2n = (int)std::ceil(std::log2(tcum / deltam));
+      const int n = 1 << log2n;
+      if (n < 32 || n > 2048 || ws > n) { gww_qfront_destroy(qf); return fail(GWW_ERR_INVALID, "qfront_create: row with %d tiles / window %d unsupported", n, ws); }
+      const int pad = n - ws;
+      const int half = (ws - 1) / 2;
+      rh.r.n = n; rh.r.log2n = log2n; rh.r.ws = ws;
+      rh.r.left = (int)((pad - 1) / 2.0);
+      rh.r.idx0 = (int)std::nearbyint((double)(-half) + 1.0 + f * duration);
+      rh.r.woff = (int)window.size();
+      rh.r.eoff = eoff;
+      rh.r.plane = ip;
+      if (rh.r.idx0 < 0 || rh.r.idx0 + ws - 1 > 1024) { gww_qfront_destroy(qf); return fail(GWW_ERR_INVALID, "qfront_create: window of f=%g exceeds the spectrum", f); }
+      // window in float32 with torch's operation order (QTile.get_window)
+      const double norm = (double)n / (duration * sample_rate) * std::sqrt(315.0 * qprime / (128.0 * f));
+      for (int i = 0; i < ws; ++i) {
+        const float wf = (float)(i - half) / (float)duration;
+        const float xf = (wf * (float)qprime) / (float)f;
+        const float a = 1.0f - xf * xf;
+        window.push_back((a * a) * (float)norm);
+      }
+      eoff += n;
+      qf->rows.push_back(rh);
+    }
+  }
+  qf->n_planes = nplanes;
+  qf->n_rows = (int)qf->rows.size();
+  qf->n_tiles = eoff;
+  // device plan
+  std::vector<QRow> orig, sorted_rows;
+  for (const QRowHost& r : qf->rows) orig.push_back(r.r);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int want = (pass == 0 ? 512 : 2048); want >= (pass == 0 ? 32 : 1024); want >>= 1)
+      for (const QRow& r : orig)
+        if (r.n == want) sorted_rows.push_back(r);
+  int n_warp = 0;
+  for (const QRow& r : sorted_rows) n_warp += (r.n <= 512) ? 1 : 0;
+  QPlan& pl = qf->plan;
+  qf->h_sorted = sorted_rows; qf->h_orig = orig; qf->h_window = window;
+  pl.n_rows = qf->n_rows; pl.n_rows_warp = n_warp; pl.n_tiles = qf->n_tiles; pl.n_planes = nplanes;
+  int maxrows = 0;
+  for (int ip = 0, r0 = 0; ip < nplanes; ++ip) {
+    int cnt = 0;
+    for (const QRow& r : orig) cnt += (r.plane == ip) ? 1 : 0;
+    pl.plane_row0[ip] = r0; pl.plane_nrows[ip] = cnt;
+    r0 += cnt;
+    if (cnt > maxrows) maxrows = cnt;
+  }
+  if (maxrows > kQiMaxRows) { gww_qfront_destroy(qf); return fail(GWW_ERR_INVALID, "qfront_create: plane with %d rows (> %d)", maxrows, kQiMaxRows); }
+  *out = qf;
+  return GWW_OK;
+}
+
+// uploads the plan tables and opts the kernels into their shared-memory sizes (first compute call)
+static int qf_ensure_device(gww_qfront* qf) {
+  if (qf->on_device) return GWW_OK;
+  GWW_TRY(gww_device_ok());
+  const double PI = 3.14159265358979323846;
+  std::vector<float2> tw(2048);
+  for (int k = 0; k < 2048; ++k)
+    tw[k] = make_float2((float)std::cos(2.0 * PI * k / 2048.0), (float)std::sin(2.0 * PI * k / 2048.0));
+  QPlan& pl = qf->plan;
+  GWW_TRY(qf_upload(qf, qf->h_sorted, &pl.rows));
+  GWW_TRY(qf_upload(qf, qf->h_orig, &pl.orig));
+  GWW_TRY(qf_upload(qf, qf->h_window, &pl.window));
+  GWW_TRY(qf_upload(qf, tw, &pl.tw2048));
+  CU_TRY(cudaFuncSetAttribute(qscan_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQsSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(qscan_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQiMaxRows * 512 * 4));
+  CU_TRY(cudaFuncSetAttribute(qadapter_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes));
+  CU_TRY(cudaFuncSetAttribute(qadapter_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3SmemBytes));
+  qf->on_device = true;
+  return GWW_OK;
+}
+
+extern "C" int gww_qfront_info(const gww_qfront_t* qf, int* n_planes, int* n_rows, int* n_tiles) {
+  if (!qf) return fail(GWW_ERR_INVALID, "qfront_info: null handle");
+  if (n_planes) *n_planes = qf->n_planes;
+  if (n_rows) *n_rows = qf->n_rows;
+  if (n_tiles) *n_tiles = qf->n_tiles;
+  return GWW_OK;
+}
+
+extern "C" int gww_qfront_plan(const gww_qfront_t* qf, double* q_of_plane, int* plane_of_row, float* freq,
+                               int* ntiles, int* windowsize, int* tile_offset) {
+  if (!qf) return fail(GWW_ERR_INVALID, "qfront_plan: null handle");
+  if (q_of_plane) for (int i = 0; i < qf->n_planes; ++i) q_of_plane[i] = qf->qs[i];
+  for (int i = 0; i < qf->n_rows; ++i) {
+    const QRowHost& r = qf->rows[i];
+    if (plane_of_row) plane_of_row[i] = r.r.plane;
+    if (freq) freq[i] = r.freq;
+    if (ntiles) ntiles[i] = r.r.n;
+    if (windowsize) windowsize[i] = r.r.ws;
+    if (tile_offset) tile_offset[i] = r.r.eoff;
+  }
+  return GWW_OK;
+}
+
+extern "C" int gww_qfront_set_adapter(gww_qfront_t* qf, const gww_qadapter_weights_t* w) {
+  if (!qf || !w) return fail(GWW_ERR_INVALID, "qfront_set_adapter: null argument");
+  if (!w->conv1_w || !w->conv1_b || !w->conv2_w || !w->conv2_b || !w->conv3_w || !w->conv3_b ||
+      !w->conv4_w || !w->conv4_b || !w->film_gamma || !w->film_beta)
+    return fail(GWW_ERR_INVALID, "qfront_set_adapter: null weight pointer");
+  if (w->n_detectors < 1 || w->n_detectors > 8)
+    return fail(GWW_ERR_INVALID, "qfront_set_adapter: n_detectors=%d out of range", w->n_detectors);
+  GWW_TRY(qf_ensure_device(qf));
+  std::vector<float> w1(9 * 16), b1(w->conv1_b, w->conv1_b + 16), w2(9 * 16 * 32), b2(w->conv2_b, w->conv2_b + 32),
+      w3(9 * 32 * 64), b3(w->conv3_b, w->conv3_b + 64), w4(w->conv4_w, w->conv4_w + 64);
+  for (int c = 0; c < 16; ++c)
+    for (int t = 0; t < 9; ++t) w1[t * 16 + c] = w->conv1_w[c * 9 + t];
+  for (int co = 0; co < 32; ++co)
+    for (int ci = 0; ci < 16; ++ci)
+      for (int t = 0; t < 9; ++t) w2[(t * 16 + ci) * 32 + co] = w->conv2_w[(co * 16 + ci) * 9 + t];
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 32; ++ci)
+      for (int t = 0; t < 9; ++t) w3[(t * 32 + ci) * 64 + co] = w->conv3_w[(co * 32 + ci) * 9 + t];
+  QAdapterDev ad{};
+  GWW_TRY(qf_upload(qf, w1, &ad.w1)); GWW_TRY(qf_upload(qf, b1, &ad.b1));
+  GWW_TRY(qf_upload(qf, w2, &ad.w2)); GWW_TRY(qf_upload(qf, b2, &ad.b2));
+  GWW_TRY(qf_upload(qf, w3, &ad.w3)); GWW_TRY(qf_upload(qf, b3, &ad.b3));
+  GWW_TRY(qf_upload(qf, w4, &ad.w4));
+  ad.b4 = w->conv4_b[0];
+  ad.scale = w->scale; ad.bias = w->bias;
+  for (int i = 0; i < 8; ++i) { ad.gamma[i] = 1.f; ad.beta[i] = 0.f; }
+  for (int i = 0; i < w->n_detectors; ++i) { ad.gamma[i] = w->film_gamma[i]; ad.beta[i] = w->film_beta[i]; }
+  qf->ad = ad;
+  qf->n_detectors = w->n_detectors;
+  qf->has_adapter = true;
+  return GWW_OK;
+}
+
+struct QWorkspace {
+  float* tiles;            // [n, n_tiles]
+  unsigned int* plane_max; // [8]
+  int* plane_idx;          // [1]
+  float* spec;             // [n, F, T]
+  float* act1;             // [n, F/2, T/2, 16]
+  float* act2;             // [n, F/4, T/4, 32]
+  float* map;              // [n, F/4, T/4]
+  size_t total;
+};
+static QWorkspace qcarve(const gww_qfront* qf, long n, uint8_t* base) {
+  QWorkspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base + o; };
+  const size_t F = qf->spec_f, T = qf->spec_t, N = (size_t)n;
+  w.tiles = (float*)take(N * qf->n_tiles * 4);
+  w.plane_max = (unsigned int*)take(64);
+  w.plane_idx = (int*)take(64);
+  w.spec = (float*)take(N * F * T * 4);
+  w.act1 = (float*)take(N * (F / 2) * (T / 2) * 16 * 4);
+  w.act2 = (float*)take(N * (F / 4) * (T / 4) * 32 * 4);
+  w.map = (float*)take(N * (F / 4) * (T / 4) * 4);
+  w.total = off;
+  return w;
+}
+extern "C" size_t gww_qfront_workspace_bytes(const gww_qfront_t* qf, long n) {
+  if (!qf || n <= 0) return 0;
+  return qcarve(qf, n, nullptr).total + 1024;
+}
+static int qcheck_ws(const gww_qfront* qf, long n, void* workspace, size_t bytes, QWorkspace* ws) {
+  if (!qf) return fail(GWW_ERR_INVALID, "null qfront handle");
+  GWW_TRY(qf_ensure_device(const_cast<gww_qfront*>(qf)));
+  if (n <= 0 || n > 65535) return fail(GWW_ERR_INVALID, "qfront: n=%ld out of range (1..65535 windows per call)", n);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  *ws = qcarve(qf, n, base);
+  const size_t need = ws->total + (size_t)(base - reinterpret_cast<uint8_t*>(workspace));
+  if (workspace == nullptr || bytes < need)
+    return fail(GWW_ERR_WORKSPACE, "qfront workspace too small: have %zu need %zu bytes", bytes, need);
+  return GWW_OK;
+}
+
+// one QScan call over n windows: tiles (all planes) -> plane choice -> spec
+static int run_qscan(const gww_qfront* qf, const float* strain, long n, long win_stride, float* spec,
+                     float* tiles, int* plane_idx, const QWorkspace& ws, cudaStream_t s) {
+  ProfScope ps(PK_QSCAN, s);
+  CU_TRY(cudaMemsetAsync(ws.plane_max, 0, 64, s));
+  qscan_tiles_kernel<<<(unsigned)n, kQsThreads, kQsSmemBytes, s>>>(strain, n, win_stride, tiles, ws.plane_max, qf->plan);
+  LAUNCH_CHECK();
+  const int R = kQiMaxRows;
+  qscan_interp_kernel<<<dim3((unsigned)n, kQiSplit), kQiThreads, (size_t)R * 512 * 4, s>>>(
+      tiles, ws.plane_max, spec, plane_idx, qf->spec_f, qf->spec_t, qf->plan);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+// adapter CNN on spec [n,F,T] -> f32 [n,80,3000] and/or bf16 time-major rows of feats_tm
+static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det, float* feats_f32,
+                        __nv_bfloat16* feats_tm, long tm_stride_w, long tm_off, const QWorkspace& ws,
+                        cudaStream_t s) {
+  if (!qf->has_adapter) return fail(GWW_ERR_INVALID, "qadapter: no adapter weights set");
+  if (det < 0 || det >= qf->n_detectors) return fail(GWW_ERR_INVALID, "qadapter: det_idx=%d out of range", det);
+  const int F = qf->spec_f, T = qf->spec_t;
+  ProfScope ps(PK_QADAPTER, s);
+  qadapter_conv1_kernel<<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
+  LAUNCH_CHECK();
+  qadapter_conv2_kernel<<<dim3(T / 32, F / 32, (unsigned)n), 256, kC2SmemBytes, s>>>(ws.act1, ws.act2, F / 2, T / 2, qf->ad);
+  LAUNCH_CHECK();
+  qadapter_conv3_kernel<<<dim3(T / 64, F / 64, (unsigned)n), 256, kC3SmemBytes, s>>>(ws.act2, ws.map, F / 4, T / 4, qf->ad);
+  LAUNCH_CHECK();
+  qadapter_pool_kernel<<<dim3((GWW_N_FRAMES + 127) / 128, (unsigned)n), 256, 0, s>>>(
+      ws.map, feats_f32, feats_tm, tm_stride_w, tm_off, F / 4, T / 4, GWW_N_MELS, GWW_N_FRAMES, det, qf->ad);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+extern "C" int gww_qscan(const gww_qfront_t* qf, const float* strain, long n, long win_stride, float* spec,
+                         float* tiles, int* plane_idx, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !spec || win_stride < 1) return fail(GWW_ERR_INVALID, "qscan: bad argument");
+  if (n == 0) return GWW_OK;
+  QWorkspace ws;
+  GWW_TRY(qcheck_ws(qf, n, workspace, workspace_bytes, &ws));
+  return run_qscan(qf, strain, n, win_stride, spec, tiles ? tiles : ws.tiles, plane_idx ? plane_idx : ws.plane_idx,
+                   ws, (cudaStream_t)stream);
+}
+
+extern "C" int gww_qadapter(const gww_qfront_t* qf, const float* spec, long n, int det_idx, float* feats_f32,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!spec || !feats_f32) return fail(GWW_ERR_INVALID, "qadapter: bad argument");
+  if (n == 0) return GWW_OK;
+  QWorkspace ws;
+  GWW_TRY(qcheck_ws(qf, n, workspace, workspace_bytes, &ws));
+  return run_qadapter(qf, spec, n, det_idx, feats_f32, nullptr, 0, 0, ws, (cudaStream_t)stream);
+}
+
+// strain windows: window b of detector i at strain + b*win_stride + i*det_stride
+static int forward_qscan_strided(const gww_model* m, const gww_qfront* qf, const float* strain, long B, int D,
+                                 long win_stride, long det_stride, int use_last_token, float* out,
+                                 const Workspace& ws, const QWorkspace& qws, cudaStream_t s) {
+  if (!m->has_head) return fail(GWW_ERR_INVALID, "forward_qscan: no head set on this model");
+  if (m->head.dims[0] != m->cfg.d_model * D)
+    return fail(GWW_ERR_INVALID, "forward_qscan: head input width %d != d_model*D = %d", m->head.dims[0],
+                m->cfg.d_model * D);
+  if (D > qf->n_detectors) return fail(GWW_ERR_INVALID, "forward_qscan: D=%d > adapter detectors %d", D, qf->n_detectors);
+  for (int i = 0; i < D; ++i) {
+    GWW_TRY(run_qscan(qf, strain + i * det_stride, B, win_stride, qws.spec, qws.tiles, qws.plane_idx, qws, s));
+    GWW_TRY(run_qadapter(qf, qws.spec, B, i, nullptr, ws.feats_tm, D, i, qws, s));
+  }
+  GWW_TRY(encoder_chunk(m, ws, (int)(B * D), nullptr, ws.pooled, use_last_token, s));
+  return run_head(m, ws.pooled, B, out, s, ws.head_scratch);
+}
+
+extern "C" int gww_forward_windows_qscan(const gww_model_t* m, const gww_qfront_t* qf, const float* strain,
+                                         long B, int D, int use_last_token, float* out, void* workspace,
+                                         size_t workspace_bytes, void* q_workspace, size_t q_workspace_bytes,
+                                         void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !out || B < 0 || D < 1) return fail(GWW_ERR_INVALID, "forward_windows_qscan: bad argument");
+  if (B == 0) return GWW_OK;
+  Workspace ws;
+  GWW_TRY(check_ws(m, (int)(B * D), workspace, workspace_bytes, &ws));
+  QWorkspace qws;
+  GWW_TRY(qcheck_ws(qf, B, q_workspace, q_workspace_bytes, &qws));
+  return forward_qscan_strided(m, qf, strain, B, D, (long)D * 2048, 2048, use_last_token, out, ws, qws,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int gww_stream_search_qscan(const gww_model_t* m, const gww_qfront_t* qf, const float* strain, int D,
+                                       long n_samples, int hop, long first_window, long n_windows, int batch,
+                                       float thr, float* scores, long* trig_idx, float* trig_score,
+                                       int* trig_count, int capacity, void* workspace, size_t workspace_bytes,
+                                       void* q_workspace, size_t q_workspace_bytes, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !scores || D < 1 || hop < 1 || n_windows < 0 || first_window < 0 || batch < 1)
+    return fail(GWW_ERR_INVALID, "stream_search_qscan: bad argument");
+  if (n_windows == 0) return GWW_OK;
+  if (n_samples < 2048 || (first_window + n_windows - 1) * hop + 2048 > n_samples)
+    return fail(GWW_ERR_INVALID, "stream_search_qscan: windows exceed the segment");
+  Workspace ws;
+  GWW_TRY(check_ws(m, batch * D, workspace, workspace_bytes, &ws));
+  QWorkspace qws;
+  GWW_TRY(qcheck_ws(qf, batch, q_workspace, q_workspace_bytes, &qws));
+  if (!m->has_head) return fail(GWW_ERR_INVALID, "stream_search_qscan: no head set");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = m->head.dims[m->head.n_layers];
+  if (C > 64) return fail(GWW_ERR_INVALID, "stream_search_qscan: head has %d outputs (> 64)", C);
+  for (long k0 = 0; k0 < n_windows; k0 += batch) {
+    const int nb = (int)((n_windows - k0 < batch) ? n_windows - k0 : batch);
+    const float* base = strain + (first_window + k0) * hop;
+    GWW_TRY(forward_qscan_strided(m, qf, base, nb, D, hop, n_samples, 1, ws.head_out, ws, qws, s));
     take_col0_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ws.head_out, C, nb, scores + k0);
     LAUNCH_CHECK();
     if (trig_idx && trig_score && trig_count)

@@ -147,6 +147,58 @@ int gww_stream_search_logmel(const gww_model_t* m, const float* strain, int D, l
 int gww_threshold_compact(const float* out, int C, long n, float thr, long idx_base, long* trig_idx,
                           float* trig_score, int* trig_count, int capacity, void* stream);
 
+/* ---- front end B: Q-transform + Q-Adapter (MLGWSC-1) --------------------------------------------- */
+/* Replaces QTransformAdapter (MLGWSC-1/inference.py:303-351) including ml4gw.transforms.QScan
+ * (:316-321, :345).  The handle holds the (q, f) tiling plan, bisquare windows and, once set, the
+ * adapter CNN weights.  Only duration * sample_rate == 2048 is supported (1 s @ 2048 Hz). */
+typedef struct gww_qfront gww_qfront_t;
+
+typedef struct {
+  const float *conv1_w, *conv1_b;   /* host [16,1,3,3], [16]   freq_adapter.0 */
+  const float *conv2_w, *conv2_b;   /* host [32,16,3,3], [32]  freq_adapter.3 */
+  const float *conv3_w, *conv3_b;   /* host [64,32,3,3], [64]  freq_adapter.6 */
+  const float *conv4_w, *conv4_b;   /* host [1,64,1,1], [1]    freq_adapter.8 */
+  float scale, bias;                /* QTransformAdapter.scale / .bias (inference.py:334-335) */
+  int n_detectors;                  /* <= 8 */
+  const float *film_gamma, *film_beta; /* host [n_detectors] (:336-337) */
+} gww_qadapter_weights_t;
+
+int gww_qfront_create(double duration, double sample_rate, double qmin, double qmax, double mismatch,
+                      int spec_f, int spec_t, gww_qfront_t** out);
+int gww_qfront_set_adapter(gww_qfront_t* qf, const gww_qadapter_weights_t* w);
+void gww_qfront_destroy(gww_qfront_t* qf);
+/* Tiling plan, for tests: counts, then per-row arrays (caller allocates n_rows entries, any may be
+ * NULL).  Rows are in plane-major, ascending-frequency order. */
+int gww_qfront_info(const gww_qfront_t* qf, int* n_planes, int* n_rows, int* n_tiles);
+int gww_qfront_plan(const gww_qfront_t* qf, double* q_of_plane, int* plane_of_row, float* freq,
+                    int* ntiles, int* windowsize, int* tile_offset);
+/* Device bytes needed by gww_qscan / gww_qadapter / gww_forward_windows_qscan on n windows. */
+size_t gww_qfront_workspace_bytes(const gww_qfront_t* qf, long n);
+/* QScan.forward on ONE call of n windows (the plane choice is coupled across the n windows, as in
+ * ml4gw).  strain: device f32, window w at strain + w*win_stride (win_stride >= 2048 or a hop for
+ * overlapping windows).  spec: device f32 [n, spec_f, spec_t].  tiles (optional, may be NULL): device
+ * f32 [n, n_tiles] normalised tile energies of all planes.  plane_idx (optional): device int. */
+int gww_qscan(const gww_qfront_t* qf, const float* strain, long n, long win_stride, float* spec,
+              float* tiles, int* plane_idx, void* workspace, size_t workspace_bytes, void* stream);
+/* freq_adapter + final_pool + scale/bias + FiLM[det_idx] on spec [n, spec_f, spec_t].
+ * feats_f32 (optional): device f32 [n, 80, 3000]. */
+int gww_qadapter(const gww_qfront_t* qf, const float* spec, long n, int det_idx, float* feats_f32,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* GWWhisperClassifier.forward (inference.py:384-392): strain device f32 [B, D, 2048] -> out [B, C].
+ * The B windows form one QScan call per detector (pass the reference's 256-window batches).
+ * workspace: gww_workspace_bytes(m, B*D); q_workspace: gww_qfront_workspace_bytes(qf, B). */
+int gww_forward_windows_qscan(const gww_model_t* m, const gww_qfront_t* qf, const float* strain, long B,
+                              int D, int use_last_token, float* out, void* workspace,
+                              size_t workspace_bytes, void* q_workspace, size_t q_workspace_bytes,
+                              void* stream);
+/* Sliding-window MLGWSC-1 search over a resident whitened segment strain [D, n_samples]: batches of
+ * `batch` consecutive windows (256 in the reference, inference.py:465), score = out[:, 0]. */
+int gww_stream_search_qscan(const gww_model_t* m, const gww_qfront_t* qf, const float* strain, int D,
+                            long n_samples, int hop, long first_window, long n_windows, int batch,
+                            float thr, float* scores, long* trig_idx, float* trig_score,
+                            int* trig_count, int capacity, void* workspace, size_t workspace_bytes,
+                            void* q_workspace, size_t q_workspace_bytes, void* stream);
+
 /* ---- building blocks exported for parity tests and profiling ----------------------------------- */
 /* C[M,N] = epilogue(A[M,K] * W[N,K]^T); A, W device bf16 row-major; epilogue ids as in
  * gemm_tc.cuh (0 bias->bf16, 1 bias+gelu->bf16, 2 bias+resid->f32, 3 bias+gelu+pos->f32). */
