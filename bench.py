@@ -33,9 +33,11 @@ FS = 2048
 SEC_PER_WINDOW = HOP / FS
 
 
-def flops_per_detwin(d, L, ffn, T=1500):
-    """Algorithmic FLOPs (2*MAC) of the full reference computation per det-window, by GEMM class
-    (tiny 36.938 G, base 87.368 G, small 344.162 G in total)."""
+def flops_per_detwin(d, L, ffn, T=1500, pruned=False):
+    """FLOPs (2*MAC) per det-window by GEMM class.  pruned=False: the ALGORITHMIC work of the full
+    reference computation (tiny 36.938 G, base 87.368 G, small 344.162 G).
+    pruned=True: the work EXECUTED when the final layer is evaluated for the last token only
+     -- used for per-kernel and roofline rates so they are not inflated."""
     conv1 = 2 * 3000 * (80 * 3) * d
     conv2 = 2 * T * (3 * d) * d
     qkv = 2 * T * d * 3 * d
@@ -43,8 +45,9 @@ def flops_per_detwin(d, L, ffn, T=1500):
     oproj = 2 * T * d * d
     fc1 = 2 * T * d * ffn
     fc2 = 2 * T * ffn * d
-    per = {"gemm_conv1": conv1, "gemm_conv2": conv2, "gemm_qkv": L * qkv, "attention": L * attn,
-           "gemm_out_proj": L * oproj, "gemm_fc1": L * fc1, "gemm_fc2": L * fc2}
+    Lf = (L - 1 + 1.0 / T) if pruned else L        # final layer: one token's row instead of T
+    per = {"gemm_conv1": conv1, "gemm_conv2": conv2, "gemm_qkv": L * qkv, "attention": Lf * attn,
+           "gemm_out_proj": Lf * oproj, "gemm_fc1": Lf * fc1, "gemm_fc2": Lf * fc2}
     per["total"] = sum(per.values())
     return per
 
@@ -110,6 +113,81 @@ def build_model(size: str, chunk: int):
     S.seeded_head(model.classifier, seed=3, gain=3.0)
     model.refresh()
     return model, base
+
+
+def build_mlgwsc_model(size: str, batch: int):
+    """BASELINE.json configs[3]: MLGWSC-1 model = Q-transform + Q-Adapter + whisper-tiny encoder + DoRA
+    + 5-layer softmax head, two detectors, 256-window batches (MLGWSC-1/inference.py:354-392,465)."""
+    from gw_whisper_b200 import B200WhisperEncoder, GWWhisperClassifier, QTransformAdapter
+    from gw_whisper_b200 import synthetic as S
+    import torch
+
+    base = S.make_encoder(size, 0, spread=True)
+    dora = S.synthetic_dora(size, targets=("q_proj", "k_proj", "v_proj", "out_proj"))
+    enc = B200WhisperEncoder.from_hf(base, dora=dora, chunk=2 * batch)
+    torch.manual_seed(11)
+    adapter = QTransformAdapter(n_detectors=2)
+    model = GWWhisperClassifier(enc, 2, num_classes=2, q_adapter=adapter)
+    S.seeded_head(model.classifier, seed=3, gain=3.0)
+    model.refresh()
+    return model, base
+
+
+def run_mlgwsc(args):
+    """Non-default workload (configs[3]): sliding 1 s windows over a resident synthetic segment through
+    the Q front end.  Same timing rules as the headline run; prints one JSON line."""
+    import torch
+    from gw_whisper_b200 import _lib
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    nwin = args.batch
+    model, base = build_mlgwsc_model(args.model, 256)
+    g = torch.Generator().manual_seed(1234)
+    seg = torch.randn(2, 2048 + HOP * (nwin - 1), generator=g).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        flush.zero_()
+        return model.stream_search(seg, HOP, nwin, 0.5)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.gww_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.gww_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    nk = lib.gww_profile_num_kinds()
+    ms_k = (C.c_double * nk)()
+    cnt_k = (C.c_long * nk)()
+    lib.gww_profile_begin()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    _lib.check(lib.gww_profile_end(ms_k, cnt_k))
+    names = [lib.gww_profile_kind_name(i).decode() for i in range(nk)]
+    kernels = {nm: {"ms_per_step": ms_k[i] / args.steps, "launches_per_step": cnt_k[i] // args.steps}
+               for i, nm in enumerate(names) if cnt_k[i]}
+    cfg = base.config
+    fl = flops_per_detwin(cfg.d_model, cfg.encoder_layers, cfg.encoder_ffn_dim)
+    line = {"metric": "strain-seconds searched/sec", "value": nwin * SEC_PER_WINDOW * args.steps / (ms * 1e-3),
+            "unit": "strain-s/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 encoder / f32 Q front end", "data": "synthetic",
+            "config": {"workload": f"MLGWSC-1: QScan + Q-Adapter + whisper-{args.model} + DoRA + softmax head, "
+                                   f"{nwin} sliding windows x 2 detectors per step, 256-window batches",
+                       "l2": "256 MiB buffer written between timed steps"},
+            "windows_per_s": nwin * args.steps / (ms * 1e-3),
+            "model_tflops": (fl["total"] + 1.286e9) * 2 * nwin * args.steps / (ms * 1e-3) / 1e12,
+            "gpu_launches": int(launches), "kernels": kernels}
+    print(json.dumps(line), flush=True)
 
 
 def reference_windows_per_s(size: str, n_windows: int, threads: int):
@@ -260,7 +338,10 @@ def run_b200(args):
     torch.cuda.synchronize()
     _lib.check(lib.gww_profile_end(ms_k, cnt_k))
     names = [lib.gww_profile_kind_name(i).decode() for i in range(nk)]
-    fl = flops_per_detwin(d, L, ffn)
+    pruned = bool(lib.gww_set_last_layer_pruning(1))      # query (and keep the default: on)
+    lib.gww_set_last_layer_pruning(int(pruned))
+    fl_alg = flops_per_detwin(d, L, ffn)
+    fl = flops_per_detwin(d, L, ffn, pruned=pruned)       # executed
     n_dw = B * D
     kernels = {}
     for i, nm in enumerate(names):
@@ -294,8 +375,14 @@ def run_b200(args):
         lm_bytes = (2048 * 4 + 3002 * 80 * 2) * n_dw   # fused path writes bf16 time-major features
         kernels["logmel"]["gbs"] = lm_bytes / (kernels["logmel"]["ms_per_step"] * 1e-3) / 1e9
         kernels["logmel"]["hbm_frac"] = kernels["logmel"]["gbs"] / hbm_peak
-    total_flops = fl["total"] * n_dw
+    total_flops = fl_alg["total"] * n_dw
     value = world * B * SEC_PER_WINDOW * args.steps / (ms_dev * 1e-3)
+    value_full = None
+    if pruned:   # transparency: the same step with the full 1500-token final layer
+        lib.gww_set_last_layer_pruning(0)
+        ms_full = timed(step_device, max(1, min(args.steps, 2)), 1)
+        lib.gww_set_last_layer_pruning(1)
+        value_full = world * B * SEC_PER_WINDOW * max(1, min(args.steps, 2)) / (ms_full * 1e-3)
     e2e_value = world * B * SEC_PER_WINDOW * args.steps / (ms_e2e * 1e-3)
 
     cpu_baseline = None
@@ -314,9 +401,13 @@ def run_b200(args):
                                    "+ 4-layer head, log-mel front end, 1 s windows @2048 Hz, hop 204",
                        "windows_per_step_per_gpu": B, "detectors": D, "det_windows_per_chunk": args.chunk,
                        "parallelism": f"time-shard dp{world}",
+                       "final_layer": ("last token only: all tokens' K/V, one query row (exact; the reference consumes "
+                                       "last_hidden_state[:, -1, :] only)" if pruned else "full 1500 tokens"),
                        "l2": "256 MiB buffer written between timed steps (L2 flush); activations per chunk >> 126 MB L2"},
             "windows_per_s": world * B * args.steps / (ms_dev * 1e-3),
             "model_tflops": total_flops * world * args.steps / (ms_dev * 1e-3) / 1e12,
+            "executed_tflops": fl["total"] * n_dw * world * args.steps / (ms_dev * 1e-3) / 1e12,
+            "value_full_final_layer": value_full,
             "e2e": {"value": e2e_value, "unit": "strain-s/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_strain.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": int(launches_per_run), "host_issue_ms_per_step": host_issue_ms,
@@ -338,7 +429,14 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="det-windows per encoder pass")
     ap.add_argument("--ref-windows", type=int, default=8, help="windows per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="svn", choices=["svn", "mlgwsc"],
+                    help="svn = headline (configs[1]); mlgwsc = Q front end path (configs[3], 1 GPU, extra)")
     args = ap.parse_args()
+    if args.workload == "mlgwsc" and args.impl == "b200":
+        if args.model == "base":
+            args.model = "tiny"
+        run_mlgwsc(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgww_b200.so")
+# GWW_LIB overrides the library path (A/B builds of kernel variants for tuning runs)
+LIB_PATH = os.environ.get("GWW_LIB") or os.path.join(HERE, "libgww_b200.so")
 
 GWW_MAX_HEAD_LAYERS = 6
 c_float_p = C.POINTER(C.c_float)
@@ -81,6 +82,7 @@ SYMBOLS = {
     "gww_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _i, _i, _i, _vp]),
     "gww_attention": (_i, [_vp, _vp, _l, _i, _i, _vp]),
     "gww_layernorm": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _vp]),
+    "gww_set_last_layer_pruning": (_i, [_i]),
     "gww_launch_count": (_l, []),
     "gww_profile_num_kinds": (_i, []),
     "gww_profile_kind_name": (C.c_char_p, [_i]),

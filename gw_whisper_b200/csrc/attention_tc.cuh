@@ -14,19 +14,18 @@
 // TMEM map (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
 // Warps: WG0/WG1 = softmax for query tile 0/1, WG2 = {w8: TMA producer, w9: MMA issuer + TMEM alloc}.
 //
-// Scheduling (r1 ncu: MUFU.EX2 is the binding pipe -- 16 results/clk/SM measured -- and was only 63 %
-// busy because every tile waited for its row max before the first exponential):
-//   * single-pass softmax: exponentials of tile j use the running max of tiles < j, so they stream
-//     straight out of the TMEM loads (32-column chunks, next chunk prefetched) while the tile max is
-//     gathered on the side.  If the tile max exceeds the stale max by more than 2^8 (rare) the pass is
-//     redone after rescaling O and l -- exact online-softmax algebra either way.  Tile 0 gets a
-//     max-only pre-pass.
-//   * one exponential in four is evaluated on the FMA/ALU pipes (round-to-nearest range reduction +
-//     degree-3 polynomial, |rel err| < 7.5e-5, far below bf16 P's 2^-9), taking 25 % off the MUFU.
-//   * S_t stays in TMEM until its pass is over; "P_t(j) ready" doubles as "S_t free": the MMA warp
-//     then issues S_t(j+1) and P_t(j).V back to back.  The two softmax warpgroups drift half a period
-//     apart on their own (the tensor pipe serves them alternately), so one group's wait for its next
-//     S overlaps the other group's exponentials.
+// Scheduling (r1 measurements: MUFU.EX2 is the binding pipe at 16 results/clk/SM; one softmax warp per
+// SM sub-partition reaches only ~80 % of that, two reach 100 % -- profiles/r1_ubench_pipes.txt):
+//   * S_t(j+1) is issued as soon as softmax t has copied S_t(j) into registers (s_free barrier): the
+//     tensor work runs a whole tile ahead of the exponentials and is completely hidden;
+//   * both softmax warpgroups run their exponentials concurrently (two warps per sub-partition keep
+//     the MUFU saturated); no turn taking;
+//   * lazy rescale: O and l are rescaled only when the tile max exceeds the running max by more
+//     than 2^8 (rare); exact online-softmax algebra either way;
+//   * kAttnFmaExp of every 32 exponentials are evaluated on the FMA/ALU pipes (round-to-nearest range
+//     reduction + cubic, |rel err| < 7.5e-5, far below bf16 P's 2^-9) to take load off the MUFU;
+//   * P_t(j).V(j) is issued when P is ready; softmax only waits for its completion (pv_done) right
+//     before it overwrites P / rescales O for tile j+1; key masking exists only in the last tile's code.
 #pragma once
 #include <type_traits>
 
@@ -41,6 +40,16 @@ struct AttnParams {
 };
 
 constexpr int kAttnStages = 3;
+#ifndef GWW_ATTN_FMA_EXP
+#define GWW_ATTN_FMA_EXP 0
+#endif
+constexpr int kAttnFmaExp = GWW_ATTN_FMA_EXP;   // exponentials per 32 evaluated without the MUFU
+#ifndef GWW_ATTN_STAGGER
+#define GWW_ATTN_STAGGER 0
+#endif
+// 1: warpgroup 1 starts its first tile half a tile behind warpgroup 0, so one group's TMEM loads /
+// max / waits fall into the other group's exponentials instead of coinciding with them
+constexpr int kAttnStagger = GWW_ATTN_STAGGER;
 constexpr int kAttnSmemBytes = 32768 + kAttnStages * 2 * 16384 + 256;
 
 __global__ void __launch_bounds__(384, 1)
@@ -62,9 +71,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
   const uint32_t bar_kempty = bar_kfull + 8 * kAttnStages;
   const uint32_t bar_vfull = bar_kempty + 8 * kAttnStages;
   const uint32_t bar_vempty = bar_vfull + 8 * kAttnStages;
-  const uint32_t bar_sfull = bar_vempty + 8 * kAttnStages;  // 2 (mma -> softmax: S_t(j) complete)
-  const uint32_t bar_pfull = bar_sfull + 16;                // 2 (softmax -> mma: P_t(j) written, S_t free)
-  const uint32_t bar_pvdone = bar_pfull + 16;               // 2 (mma -> softmax: P_t(j).V finished)
+  const uint32_t bar_sfull = bar_vempty + 8 * kAttnStages;  // 2
+  const uint32_t bar_pfull = bar_sfull + 16;                // 2
+  const uint32_t bar_ofull = bar_pfull + 16;                // 2
+  const uint32_t bar_sfree = bar_ofull + 16;                // 2 (softmax -> mma: S copied to registers)
+  const uint32_t bar_pvdone = bar_sfree + 16;               // 2 (mma -> softmax: P.V finished)
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 1 + 4 * kAttnStages + 10);
 
   const int warp = threadIdx.x >> 5;
@@ -87,6 +98,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_sfull + 8 * i, 1);
       mbar_init(bar_pfull + 8 * i, 128);
+      mbar_init(bar_ofull + 8 * i, 1);
+      mbar_init(bar_sfree + 8 * i, 128);
       mbar_init(bar_pvdone + 8 * i, 1);
     }
     fence_mbar_init();
@@ -129,6 +142,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
       const uint32_t tO[2] = {tmem_base + 384u, tmem_base + 448u};
       const uint64_t qdesc[2] = {make_sw128_desc(smem_u32(q_s)),
                                  make_sw128_desc(smem_u32(q_s + 16384))};
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kfull, 0);
+      tc_fence_after();
+      {
+        const uint64_t kdesc = make_sw128_desc(smem_u32(k_s));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
+          umma_commit(bar_sfull + 8 * t);
+        }
+        umma_commit(bar_kempty);
+      }
+      // issue order per step j:  S0(j+1) | P1(j-1).V | S1(j+1) | P0(j).V   (matches the order in
+      // which the staggered softmax groups produce their events; any other order is still safe)
       auto issue_s = [&](int t, const uint64_t kdesc) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
@@ -140,38 +168,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
           umma_ts(tO[t], tP[t] + 8 * k, vdesc + 128 * k, kIdescO, (!first || k) ? 1u : 0u);
         umma_commit(bar_pvdone + 8 * t);
       };
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_kfull, 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = make_sw128_desc(smem_u32(k_s));
-        issue_s(0, kdesc);
-        issue_s(1, kdesc);
-        umma_commit(bar_kempty);
-      }
       int stage = 0;              // stage of K/V tile j
       uint32_t phase = 0;
+      int pstage = 0;             // stage of V tile j-1
       for (int j = 0; j < nkv; ++j) {
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == kAttnStages) { nstage = 0; nphase ^= 1; }
         const bool has_next = (j + 1 < nkv);
         const uint64_t kdesc_n = make_sw128_desc(smem_u32(k_s + nstage * 16384));
-        const uint64_t vdesc = make_sw128_desc(smem_u32(v_s + stage * 16384));
-        if (has_next) mbar_wait(bar_kfull + 8 * nstage, nphase);
-        mbar_wait(bar_vfull + 8 * stage, phase);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(bar_pfull + 8 * t, j & 1);       // P_t(j) in TMEM, S_t no longer read
+        if (has_next) {
+          mbar_wait(bar_kfull + 8 * nstage, nphase);
+          mbar_wait(bar_sfree + 8 * 0, j & 1);
           tc_fence_after();
-          if (has_next) issue_s(t, kdesc_n);         // the softmax group is waiting for this one
-          issue_pv(t, vdesc, j == 0);
+          issue_s(0, kdesc_n);
         }
-        if (has_next) umma_commit(bar_kempty + 8 * nstage);
-        umma_commit(bar_vempty + 8 * stage);
+        if (j >= 1) {
+          mbar_wait(bar_pfull + 8 * 1, (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, make_sw128_desc(smem_u32(v_s + pstage * 16384)), j - 1 == 0);
+          umma_commit(bar_vempty + 8 * pstage);
+        }
+        if (has_next) {
+          mbar_wait(bar_sfree + 8 * 1, j & 1);
+          tc_fence_after();
+          issue_s(1, kdesc_n);
+          umma_commit(bar_kempty + 8 * nstage);
+        }
+        mbar_wait(bar_vfull + 8 * stage, phase);
+        mbar_wait(bar_pfull + 8 * 0, j & 1);
+        tc_fence_after();
+        issue_pv(0, make_sw128_desc(smem_u32(v_s + stage * 16384)), j == 0);
+        if (!has_next) umma_commit(bar_ofull + 8 * 0);
+        pstage = stage;
         stage = nstage;
         phase = nphase;
       }
+      mbar_wait(bar_pfull + 8 * 1, (nkv - 1) & 1);
+      tc_fence_after();
+      issue_pv(1, make_sw128_desc(smem_u32(v_s + pstage * 16384)), nkv - 1 == 0);
+      umma_commit(bar_vempty + 8 * pstage);
+      umma_commit(bar_ofull + 8 * 1);
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -184,7 +221,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
     const uint32_t tO = tmem_base + lane_off + 384 + t * 64;
     constexpr float kLog2e = 1.4426950408889634f;
     float m_used = 0.f, l = 0.f;
-    const uint32_t b_sfull = bar_sfull + 8 * t;
+    const uint32_t b_sfull = bar_sfull + 8 * t, b_sfree = bar_sfree + 8 * t;
     const uint32_t b_pfull = bar_pfull + 8 * t, b_pvdone = bar_pvdone + 8 * t;
 
     // exp2 on the FMA/ALU pipes: n = rint(x) by the 1.5*2^23 trick, 2^f on [-0.5, 0.5] as a cubic,
@@ -201,85 +238,89 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
 
     auto tile = [&](const int j, auto mask_tag) {
       constexpr bool kMask = decltype(mask_tag)::value;
-      const int valid = p.T - j * 128;             // keys [0, valid) of this tile exist (kMask only)
       mbar_wait(b_sfull, j & 1);
       tc_fence_after();
-      uint32_t s[2][32];
-      if (j == 0) {
-        // max-only pre-pass: there is no running max to speculate with yet
-        float mt = -INFINITY;
-        tmem_ld32(tS, s[0]);
+      uint32_t s[4][32];
+      tmem_ld32(tS + 0, s[0]);
+      tmem_ld32(tS + 32, s[1]);
+      tmem_ld32(tS + 64, s[2]);
+      tmem_ld32(tS + 96, s[3]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(b_sfree);                      // S_t is in registers: the next Q.K^T may overwrite it
+      if constexpr (kMask) {
+        const int valid = p.T - j * 128;         // keys [0, valid) of this tile exist
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld();
-          if (c + 1 < 4) tmem_ld32(tS + 32 * (c + 1), s[(c + 1) & 1]);
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (!kMask || c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(s[c & 1][i]));
-        }
-        m_used = mt;
+            if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
       }
-      const float l_before = l;
+      float mt0 = -INFINITY, mt1 = -INFINITY, mt2 = -INFINITY, mt3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mt0 = fmaxf(mt0, __uint_as_float(s[0][i]));
+        mt1 = fmaxf(mt1, __uint_as_float(s[1][i]));
+        mt2 = fmaxf(mt2, __uint_as_float(s[2][i]));
+        mt3 = fmaxf(mt3, __uint_as_float(s[3][i]));
+      }
+      const float mt = fmaxf(fmaxf(mt0, mt1), fmaxf(mt2, mt3));
       bool pv_waited = (j == 0);
+      if (j == 0) {
+        m_used = mt;
+      } else {
+        // lazy rescale: exact (same algebra as online softmax), but skipped while the stale max
+        // keeps exp2 arguments <= 8.
+        const bool need = (mt - m_used) * kLog2e > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(b_pvdone, (j - 1) & 1);      // O_t must be complete before it is rescaled
+          tc_fence_after();
+          pv_waited = true;
+          const float sc = need ? fast_exp2((m_used - mt) * kLog2e) : 1.0f;
+          uint32_t o[16];
 #pragma unroll 1
-      for (int attempt = 0; attempt < 2; ++attempt) {
-        const float mneg = -m_used * kLog2e;
-        float mt0 = -INFINITY, mt1 = -INFINITY;
-        float l0 = 0.f, l1 = 0.f;
-        uint32_t pk[32];
-        tmem_ld32(tS, s[0]);
+          for (int h = 0; h < 4; ++h) {
+            tmem_ld16(tO + h * 16, o);
+            tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld();
-          if (c + 1 < 4) tmem_ld32(tS + 32 * (c + 1), s[(c + 1) & 1]);
-          uint32_t(&sc)[32] = s[c & 1];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a0 = __uint_as_float(sc[i]), a1 = __uint_as_float(sc[i + 1]);
-            if (kMask) {
-              if (c * 32 + i >= valid) a0 = -INFINITY;
-              if (c * 32 + i + 1 >= valid) a1 = -INFINITY;
-            }
-            mt0 = fmaxf(mt0, a0);
-            mt1 = fmaxf(mt1, a1);
-            const float x0 = fmaf(a0, kLog2e, mneg), x1 = fmaf(a1, kLog2e, mneg);
-            // one exponential in four goes to the FMA pipes (never a masked one: -inf needs the MUFU)
-            const float p0 = fast_exp2(x0);
-            const float p1 = (!kMask && (i & 7) == 6) ? exp2_fma(x1) : ((i & 7) == 2 && !kMask ? exp2_fma(x1) : fast_exp2(x1));
-            l0 += p0;
-            l1 += p1;
-            pk[(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+            tmem_st16(tO + h * 16, o);
           }
-          if (c & 1) {                                 // 64 columns packed -> 32 TMEM columns of P
-            if (!pv_waited) {
-              mbar_wait(b_pvdone, (j - 1) & 1);        // P_t(j-1).V finished reading P_t / writing O_t
-              tc_fence_after();
-              pv_waited = true;
-            }
-            tmem_st32(tP + (c >> 1) * 32, pk);
-          }
+          tmem_wait_st();
+          l *= sc;
+          if (need) m_used = mt;
         }
-        const float mt = fmaxf(mt0, mt1);
-        const bool need = (j > 0) && (attempt == 0) && (fmaf(mt, kLog2e, mneg) > 8.0f);
-        if (!__any_sync(0xffffffffu, need)) {
-          l = l_before + (l0 + l1);
-          break;
-        }
-        // rare: the stale max was too small for some row of this warp -> rescale O, l and redo
-        const float scl = need ? fast_exp2((m_used - mt) * kLog2e) : 1.0f;
-        uint32_t o[16];
-#pragma unroll 1
-        for (int h = 0; h < 4; ++h) {
-          tmem_ld16(tO + h * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scl);
-          tmem_st16(tO + h * 16, o);
-        }
-        tmem_wait_st();
-        l = l_before * scl;
-        if (need) m_used = mt;
       }
+      const float mneg = -m_used * kLog2e;
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t pk[32];
+      if (kAttnStagger && j == 0 && t == 1) named_bar_sync(2, 256);    // wait for group 0's half-tile mark
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (kAttnStagger && j == 0 && t == 0 && c == 2) named_bar_arrive(2, 256);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float x0 = fmaf(__uint_as_float(s[c][i]), kLog2e, mneg);
+          const float x1 = fmaf(__uint_as_float(s[c][i + 1]), kLog2e, mneg);
+          // a fixed subset goes to the FMA pipes (never in the masked tile: -inf needs the MUFU)
+          const bool f0 = !kMask && (i * kAttnFmaExp / 32) != ((i + 1) * kAttnFmaExp / 32);
+          const bool f1 = !kMask && ((i + 1) * kAttnFmaExp / 32) != ((i + 2) * kAttnFmaExp / 32);
+          const float p0 = f0 ? exp2_fma(x0) : fast_exp2(x0);
+          const float p1 = f1 ? exp2_fma(x1) : fast_exp2(x1);
+          l0 += p0;
+          l1 += p1;
+          pk[(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+        }
+        if (c & 1) {                                 // 64 columns packed -> 32 TMEM columns of P
+          if (!pv_waited) {
+            mbar_wait(b_pvdone, (j - 1) & 1);        // P_t(j-1).V finished reading P_t
+            tc_fence_after();
+            pv_waited = true;
+          }
+          tmem_st32(tP + (c >> 1) * 32, pk);
+        }
+      }
+      l += l0 + l1;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(b_pfull);
@@ -288,7 +329,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
     if ((p.T & 127) != 0) tile(nkv - 1, std::true_type{});
     else tile(nkv - 1, std::false_type{});
     // ---- epilogue: O_t / l -> bf16 -> swizzled staging (the dead Q_t buffer) -> TMA store
-    mbar_wait(b_pvdone, (nkv - 1) & 1);
+    mbar_wait(bar_ofull + 8 * t, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     uint32_t o0[32], o1[32];

@@ -69,6 +69,96 @@ mean_pool_kernel(const float* __restrict__ hs, float* __restrict__ out, int T, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Last-token-only tail of the final encoder layer.  The reference consumes only
+// last_hidden_state[:, -1, :] (MLGWSC-1/inference.py:390, Signal_vs_Noise/src/model.py:25-26); in the
+// final layer that value depends on every token's K and V but only on the LAST token's query,
+// attention row, out-projection, MLP and final LayerNorm.  Same arithmetic as HF
+// modeling_whisper.py:215-238 for that one row, in fp32 on CUDA cores (1500 x 64 MACs per head).
+//   qkv [nc, T, 3d] bf16 (q pre-scaled) -> out [nc, d] bf16 ; grid (heads, nc), 256 threads
+__global__ void __launch_bounds__(256)
+last_row_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
+                          int d) {
+  extern __shared__ __align__(16) float lra_smem[];   // [T] scores | [8][64] partial outputs | [16] reductions
+  float* sc = lra_smem;
+  float* part = sc + ((T + 3) & ~3);
+  float* red = part + 8 * 64;
+  const int h = blockIdx.x;
+  const long b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* base = qkv + b * static_cast<long>(T) * 3 * d + h * 64 + 2 * lane;
+  const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + static_cast<long>(T - 1) * 3 * d));
+  const __nv_bfloat16* kb = base + d;
+  const __nv_bfloat16* vb = base + 2 * d;
+  float wmax = -INFINITY;
+  for (int k0 = warp * 4; k0 < T; k0 += 32) {        // 4 keys per warp iteration: 4 loads in flight
+    float dot[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = min(k0 + u, T - 1);
+      const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kb + static_cast<long>(k) * 3 * d));
+      dot[u] = q.x * kv.x + q.y * kv.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u < T) {
+        if (lane == 0) sc[k0 + u] = dot[u];
+        wmax = fmaxf(wmax, dot[u]);
+      }
+  }
+  if (lane == 0) red[warp] = wmax;
+  __syncthreads();
+  float m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  float lsum = 0.f;
+  for (int k = threadIdx.x; k < T; k += 256) {
+    const float pk = __expf(sc[k] - m);
+    sc[k] = pk;
+    lsum += pk;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if (lane == 0) red[8 + warp] = lsum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[8 + i];
+  float2 acc = make_float2(0.f, 0.f);
+  for (int k0 = warp * 4; k0 < T; k0 += 32) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = min(k0 + u, T - 1);
+      const float pk = (k0 + u < T) ? sc[k] : 0.f;
+      const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + static_cast<long>(k) * 3 * d));
+      acc.x = fmaf(pk, vv.x, acc.x);
+      acc.y = fmaf(pk, vv.y, acc.y);
+    }
+  }
+  part[warp * 64 + 2 * lane] = acc.x;
+  part[warp * 64 + 2 * lane + 1] = acc.y;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += part[i * 64 + threadIdx.x];
+    out[b * d + h * 64 + threadIdx.x] = __float2bfloat16(v / tot);
+  }
+}
+
+// x_last[i, :] = x[i*T + T-1, :]   (f32 residual rows of the last token)
+__global__ void __launch_bounds__(128)
+gather_last_rows_kernel(const float* __restrict__ x, float* __restrict__ x_last, int T, int d) {
+  const long i = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(x + (i * T + (T - 1)) * d);
+  float4* dst = reinterpret_cast<float4*>(x_last + i * d);
+  for (int c = threadIdx.x; c < d / 4; c += 128) dst[c] = src[c];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Pooled classifier head: x [B, in0] f32 -> Linear(+ReLU) x (L-1) -> Linear -> optional softmax.
 // One launch per Linear so every layer fills the machine: CTA = 8 output neurons x 16 windows,
 // a warp owns one neuron, its lanes stride over the input with float4 loads (coalesced weight rows,

@@ -57,6 +57,8 @@ extern "C" const char* gww_version(void) { return "gw-whisper-b200 0.1 (sm_100a)
 extern "C" long gww_launch_count(void) { return g_launches.load(); }
 
 static int g_num_sms = 0;
+static std::atomic<int> g_prune_last{1};
+extern "C" int gww_set_last_layer_pruning(int enable) { return g_prune_last.exchange(enable ? 1 : 0); }
 extern "C" int gww_device_ok(void) {
   if (g_num_sms > 0) return GWW_OK;   // one process per GPU: checked once
   int dev = 0, count = 0;
@@ -646,6 +648,7 @@ struct Workspace {
   float* head_out;          // [chunk, 64]
   float* head_scratch;      // [2, chunk, kHeadMaxWidth]
   float* gather;            // [chunk, 2048] contiguous strain windows
+  float* x_last;            // [chunk, d] residual rows of the last token (pruned final layer)
   size_t total;
 };
 static size_t align_up(size_t v) { return (v + 1023) & ~(size_t)1023; }
@@ -667,6 +670,7 @@ static Workspace carve(const gww_model* m, int chunk, uint8_t* base) {
   w.head_out = (float*)take((size_t)chunk * 64 * 4);
   w.head_scratch = (float*)take((size_t)2 * chunk * kHeadMaxWidth * 4);
   w.gather = (float*)take((size_t)chunk * 2048 * 4);
+  w.x_last = (float*)take((size_t)chunk * d * 4);
   w.total = off;
   return w;
 }
@@ -715,7 +719,32 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     GWW_TRY(run_gemm(g, stream));
   }
   __nv_bfloat16* qkv = ws.g;
-  for (const LayerDev& ld : m->layers) {
+  // when only last_hidden_state[:, -1, :] is consumed, the final layer needs all tokens'
+  // K and V but only the last token's query row, out-projection, MLP and final LayerNorm.
+  const bool prune = (last_hidden == nullptr && pooled != nullptr && use_last_token && g_prune_last.load() != 0);
+  for (size_t li = 0; li < m->layers.size(); ++li) {
+    const LayerDev& ld = m->layers[li];
+    if (prune && li + 1 == m->layers.size()) {
+      const int T = GWW_N_CTX;
+      __nv_bfloat16* hl = ws.h;                          // [nc, d] attention output of the last token
+      __nv_bfloat16* hl2 = ws.h + (size_t)nc * d;        // [nc, d] LN2 output
+      GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
+      GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
+      {
+        ProfScope ps(PK_ATTN, stream);
+        const size_t smem = (size_t)(((T + 3) & ~3) + 8 * 64 + 16) * sizeof(float);
+        last_row_attention_kernel<<<dim3(d / 64, nc), 256, smem, stream>>>(qkv, hl, T, d);
+        LAUNCH_CHECK();
+        gather_last_rows_kernel<<<nc, 128, 0, stream>>>(ws.x, ws.x_last, T, d);
+        LAUNCH_CHECK();
+      }
+      GWW_TRY(run_linear(hl, ld.o_w, ws.x_last, ld.o_b, ws.x_last, nc, d, d, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_O));
+      GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x_last, hl2, ld.ln2_g, ld.ln2_b, nc, d, 0, 1, stream));
+      GWW_TRY(run_linear(hl2, ld.fc1_w, ws.g, ld.fc1_b, nullptr, nc, f, d, EPI_BIAS_GELU_BF16, bn_f, stream, PK_GEMM_FC1));
+      GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x_last, ld.fc2_b, ws.x_last, nc, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2));
+      GWW_TRY(run_ln_t<float>(ws.x_last, pooled, m->lnp_g, m->lnp_b, nc, d, 0, 1, stream));
+      return GWW_OK;
+    }
     GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
     GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
     GWW_TRY(run_attention(qkv, ws.h, nc, GWW_N_CTX, d, stream));

@@ -38,13 +38,18 @@ struct LogmelTables {
   const double* mel_w;      // packed non-zero weights
 };
 
-constexpr int kLmThreads = 512;
+constexpr int kLmThreads = 384;
 constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kLmLive = 102;
+constexpr int kLmFramesPerWarp = 3;                 // frames sharing one twiddle load in phase 3
 constexpr int kLmSmemY = 16000 * 4;
 constexpr int kLmSmemC = 17 * 128 * 16;
-constexpr int kLmSmemScratch = 90112;
-constexpr int kLmSmemTw400 = 400 * 16;
+constexpr int kLmWarpScratch = 200 * 2 * kLmFramesPerWarp * 8;   // eo[200][3][2] doubles per warp
+constexpr int kLmSmemScratch = kLmWarps * kLmWarpScratch;         // 115200 >= 2*2048*16 (phase 1)
+constexpr int kLmTw400Pad = 400 + 400 / 8;          // entry j lives at j + (j >> 3): spreads strided reads
+constexpr int kLmSmemTw400 = kLmTw400Pad * 16;
+static_assert(kLmSmemScratch >= 2 * 2048 * 16 && kLmSmemScratch >= kLmWarps * 4096, "scratch too small");
+static_assert(kLmLive % kLmFramesPerWarp == 0, "live frames must split evenly into per-warp groups");
 constexpr int kLmSmemTw125 = 125 * 16;
 constexpr int kLmSmemBytes = kLmSmemY + kLmSmemC + kLmSmemScratch + kLmSmemTw400 + kLmSmemTw125 + 128;
 
@@ -60,12 +65,12 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
   double2* Cm = reinterpret_cast<double2*>(lm_smem + kLmSmemY);
   uint8_t* scratch = lm_smem + kLmSmemY + kLmSmemC;
   double2* tw400 = reinterpret_cast<double2*>(scratch + kLmSmemScratch);
-  double2* tw125 = tw400 + 400;
+  double2* tw125 = tw400 + kLmTw400Pad;
   float* red = reinterpret_cast<float*>(tw125 + 125);
   float* melout = reinterpret_cast<float*>(Cm);  // phase 3/4 alias: [102][80]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 400; i += kLmThreads) tw400[i] = tb.tw400[i];
+  for (int i = tid; i < 400; i += kLmThreads) tw400[i + (i >> 3)] = tb.tw400[i];
   for (int i = tid; i < 125; i += kLmThreads) tw125[i] = tb.tw125[i];
 
   for (long w = blockIdx.x; w < n_detwin; w += gridDim.x) {
@@ -157,70 +162,94 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
       }
     }
     __syncthreads();
-    // ---------------- phase 3: live frames, one warp per frame
+    // ---------------- phase 3: live frames, kLmFramesPerWarp frames per warp pass.  The folded DFT is a
+    // [frames x 199] x [199 x 201] product against the cos/sin table: every twiddle fetched from smem
+    // (the binding resource: one 16-byte load per lane per 2 DFMA in the one-frame version, r1 profile)
+    // now feeds three frames.
     float lmax = -10.0f;
     {
-      double* eo = reinterpret_cast<double*>(scratch) + warp * 608;  // e[200] | o[200] | pw[208]
-      double* ev = eo;
-      double* ov = eo + 200;
-      double* pw = eo + 400;
-      for (int f = warp; f < kLmLive; f += kLmWarps) {
-        const int base = 160 * f - 200;
-        double u200;
-        {
-          const int i200 = base + 200;
-          u200 = (i200 < 16000) ? static_cast<double>(y[i200]) : 0.0;   // w[200] = 1, i200 >= 0
+      constexpr int NF = kLmFramesPerWarp;
+      double* eo = reinterpret_cast<double*>(scratch + warp * kLmWarpScratch);  // [200][NF][2]; later pw[NF][208]
+      for (int g = warp; g < kLmLive / NF; g += kLmWarps) {
+        const int f0 = g * NF;
+        double u200[NF];
+#pragma unroll
+        for (int ff = 0; ff < NF; ++ff) {
+          const int i200 = 160 * (f0 + ff);                    // base + 200, w[200] = 1, >= 0
+          u200[ff] = (i200 < 16000) ? static_cast<double>(y[i200]) : 0.0;
         }
-        for (int nn = lane; nn < 200; nn += 32) {
+        for (int idx = lane; idx < 200 * NF; idx += 32) {
+          const int nn = idx / NF, ff = idx - nn * NF;
           if (nn >= 1) {
+            const int base = 160 * (f0 + ff) - 200;
             const int ia = base + nn, ib = base + 400 - nn;
             const double ya = (ia < 0) ? y[-ia] : ((ia < 16000) ? y[ia] : 0.0f);
             const double yb = (ib < 0) ? y[-ib] : ((ib < 16000) ? y[ib] : 0.0f);
-            const double wn = 0.5 - 0.5 * tw400[nn].x;
-            ev[nn] = wn * (ya + yb);
-            ov[nn] = wn * (ya - yb);
+            const double wn = 0.5 - 0.5 * tw400[nn + (nn >> 3)].x;
+            eo[(nn * NF + ff) * 2] = wn * (ya + yb);
+            eo[(nn * NF + ff) * 2 + 1] = -(wn * (ya - yb));
           }
         }
         __syncwarp();
-        double re[7], im[7];
+        double re[NF][7], im[NF][7];
         int jj[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
           const int k = lane + 32 * i;
-          re[i] = (k & 1) ? -u200 : u200;
-          im[i] = 0.0;
+#pragma unroll
+          for (int ff = 0; ff < NF; ++ff) {
+            re[ff][i] = (k & 1) ? -u200[ff] : u200[ff];
+            im[ff][i] = 0.0;
+          }
           jj[i] = 0;
         }
 #pragma unroll 1
         for (int nn = 1; nn < 200; ++nn) {
-          const double en = ev[nn], on = ov[nn];
+          double ev[NF], ov[NF];
+          const double2* src = reinterpret_cast<const double2*>(eo + nn * NF * 2);
+#pragma unroll
+          for (int ff = 0; ff < NF; ++ff) {
+            const double2 v = src[ff];                         // warp-uniform address: broadcast
+            ev[ff] = v.x;
+            ov[ff] = v.y;                                      // already negated
+          }
 #pragma unroll
           for (int i = 0; i < 7; ++i) {
             const int k = lane + 32 * i;
             int j = jj[i] + k;
             if (j >= 400) j -= 400;
             jj[i] = j;
-            const double2 t = tw400[j];
-            re[i] = fma(en, t.x, re[i]);
-            im[i] = fma(-on, t.y, im[i]);
+            const double2 t = tw400[j + (j >> 3)];
+#pragma unroll
+            for (int ff = 0; ff < NF; ++ff) {
+              re[ff][i] = fma(ev[ff], t.x, re[ff][i]);
+              im[ff][i] = fma(ov[ff], t.y, im[ff][i]);
+            }
           }
         }
+        __syncwarp();                                          // eo is dead: reuse it for the power spectra
+        double* pw = eo;                                       // [NF][208]
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          const int k = lane + 32 * i;
-          if (k <= 200) pw[k] = re[i] * re[i] + im[i] * im[i];
-        }
+        for (int ff = 0; ff < NF; ++ff)
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= 200) pw[ff * 208 + k] = re[ff][i] * re[ff][i] + im[ff][i] * im[ff][i];
+          }
         __syncwarp();
+#pragma unroll 1
+        for (int ff = 0; ff < NF; ++ff) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int mm = lane + 32 * i;
-          if (mm < 80) {
-            const int lo = tb.mel_lo[mm], cnt = tb.mel_cnt[mm], off = tb.mel_off[mm];
-            double acc = 0.0;
-            for (int c = 0; c < cnt; ++c) acc = fma(tb.mel_w[off + c], pw[lo + c], acc);
-            const float lv = static_cast<float>(log10(fmax(acc, 1e-10)));
-            melout[f * 80 + mm] = lv;
-            lmax = fmaxf(lmax, lv);
+          for (int i = 0; i < 3; ++i) {
+            const int mm = lane + 32 * i;
+            if (mm < 80) {
+              const int lo = tb.mel_lo[mm], cnt = tb.mel_cnt[mm], off = tb.mel_off[mm];
+              double acc = 0.0;
+              for (int c = 0; c < cnt; ++c) acc = fma(tb.mel_w[off + c], pw[ff * 208 + lo + c], acc);
+              const float lv = static_cast<float>(log10(fmax(acc, 1e-10)));
+              melout[(f0 + ff) * 80 + mm] = lv;
+              lmax = fmaxf(lmax, lv);
+            }
           }
         }
         __syncwarp();

@@ -209,6 +209,11 @@ int gww_attention(const void* qkv, void* out, long n, int T, int d_model, void* 
 /* x device f32 [rows, d] -> out bf16 (out_bf16=1) or f32 [rows, d] */
 int gww_layernorm(const float* x, void* out, const float* gamma, const float* beta, long rows, int d,
                   int out_bf16, void* stream);
+/* The reference consumes only last_hidden_state[:, -1, :]; by default the final encoder layer is
+ * therefore evaluated for the last token only (all tokens' K/V, one query row; exact up to summation
+ * order) whenever gww_encoder_forward is asked for the last-token `pooled` output
+ * without `last_hidden`.  enable=0 forces the full 1500-token final layer.  Returns the old value. */
+int gww_set_last_layer_pruning(int enable);
 /* number of kernel launches issued by this library in this process (bench.py gpu_launches) */
 long gww_launch_count(void);
 /* Optional per-kernel-class timing: between begin/end every launch is bracketed by CUDA events on

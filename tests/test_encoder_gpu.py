@@ -48,8 +48,12 @@ def test_encoder_last_hidden_state(size, spread):
     assert got.shape == ref.shape
     e, _ = _stats(f"last_hidden[{size},spread={spread}]", got, ref)
     e_last, sp = _stats(f"last_token[{size},spread={spread}]", got[:, -1], ref[:, -1])
+    # the pooled path evaluates the final layer for the last token only: same value as
+    # token 1499 of the full computation up to summation order / bf16 rounding of that one row
     pooled = enc.pooled(feats.to(dev)).cpu()
-    assert torch.allclose(pooled, got[:, -1], atol=1e-5)
+    e_pool, _ = _stats(f"pooled(last token)[{size},spread={spread}] vs oracle", pooled, ref[:, -1])
+    assert (pooled - got[:, -1]).abs().max().item() < 3e-2
+    assert e_pool < 1.5 * yard.max().item() + 2e-2
     mean_pooled = enc.pooled(feats.to(dev), use_last_token=False).cpu()
     assert torch.allclose(mean_pooled, got.mean(1), atol=1e-4)
     # LayerNorm'd outputs are O(1).  Gate: no worse than 1.5x PyTorch's own bf16 autocast of the
@@ -57,6 +61,33 @@ def test_encoder_last_hidden_state(size, spread):
     assert e < 1.5 * yard.max().item() + 2e-2, "encoder hidden states off"
     assert (got - ref).abs().mean().item() < 1.5 * yard.mean().item() + 2e-3
     assert e_last < 1.5 * yard.max().item() + 2e-2
+
+
+def test_last_token_pruning_matches_full_final_layer():
+    """the last-token-only evaluation of the final layer (default) must give the same
+    pooled representation as running the full 1500-token final layer and selecting token 1499."""
+    from oracle import encoder as E, logmel as L
+    from gw_whisper_b200 import B200WhisperEncoder, _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    base = E.make_encoder("tiny", 0, spread=True)
+    enc = B200WhisperEncoder.from_hf(base, chunk=4)
+    feats = torch.from_numpy(L.logmel_restated(_strain(5)[:, 0].numpy())).to(dev)
+    with torch.no_grad():
+        ref = base.to(dev)(feats).last_hidden_state[:, -1, :].cpu()
+    old = lib.gww_set_last_layer_pruning(1)
+    try:
+        pruned = enc.pooled(feats).cpu()
+        lib.gww_set_last_layer_pruning(0)
+        full = enc.pooled(feats).cpu()
+        from_hidden = enc(feats).last_hidden_state[:, -1, :].cpu()
+    finally:
+        lib.gww_set_last_layer_pruning(old)
+    e_pf, _ = _stats("pooled pruned vs full final layer", pruned, full)
+    e_p, _ = _stats("pooled pruned vs fp32 oracle", pruned, ref)
+    e_f, _ = _stats("pooled full vs fp32 oracle", full, ref)
+    assert torch.equal(full, from_hidden)
+    assert e_pf < 3e-2 and e_p < 1.2 * max(e_f, 2e-2)
 
 
 def test_encoder_rejects_bad_length():
@@ -97,7 +128,9 @@ def test_two_channel_model_with_dora(spread):
     e2, _ = _stats(f"two_channel module logits (spread={spread})", got_mod, ref)
     yard = (_bf16_yardstick(ref_model.to(dev), feats[:, 0].to(dev), feats[:, 1].to(dev)).cpu() - ref).abs().max().item()
     print(f"torch bf16-autocast yardstick on logits: {yard:.4e}")
-    assert e1 < 2e-2 and e2 < 2e-2
+    # 2e-2 absolute, or -- when PyTorch's own bf16 autocast of the reference model is already at that
+    # level on these (deliberately ill-conditioned, spread-scaled) weights -- within 1.5x of it
+    assert (e1 < 2e-2 and e2 < 2e-2) or max(e1, e2) < 1.5 * yard
     if spread:
         assert sp > 5e-3, "spread-scaled weights should give logits that move with the input"
     # thresholded decisions agree away from a guard band around the threshold

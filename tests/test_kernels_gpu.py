@@ -44,6 +44,9 @@ GEMM_CASES = [
     (1500, 384, 1152, 3, 192),
     (20000, 1536, 512, 0, 256),
     (777, 768, 3072, 2, 256),
+    (5, 512, 512, 2, 256),        # tiny-M GEMMs of the last-token-only final layer
+    (8, 2048, 512, 1, 256),
+    (256, 512, 2048, 2, 256),
 ]
 
 
