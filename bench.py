@@ -366,11 +366,37 @@ def run_b200(args):
         hbm_peak = float(peaks.get("hbm_gbs", hbm_peak))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all encoder GEMMs)", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-                "peak_source": peak_src,
-                "flops_per_launch": gemm_flops / max(gemm_launches, 1),
-                "avg_launch_ms": gemm_ms / max(gemm_launches, 1)}
+    ncu_traffic = {}
+    tr_path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tr_path):
+        ncu_traffic = json.load(open(tr_path))
+
+    def traffic_of(key):
+        """dram read+write bytes per launch from the committed ncu --set full capture (same model,
+        256 det-windows per launch); None when the bench runs another geometry."""
+        ent = ncu_traffic.get(key)
+        if not ent or args.model != "base" or args.chunk != ent.get("det_windows"):
+            return None
+        return ent["dram_bytes_per_launch"]
+
+    roofline_gemm = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all encoder GEMMs)", "achieved": achieved,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": {k: traffic_of(k) for k in ("gemm_qkv", "gemm_out_proj", "gemm_fc1", "gemm_fc2")},
+                     "peak_source": peak_src, "flops_per_launch": gemm_flops / max(gemm_launches, 1),
+                     "avg_launch_ms": gemm_ms / max(gemm_launches, 1)}
+    # the single kernel with the largest share of the step is the fused attention
+    ia = names.index("attention")
+    att_ms, att_n = ms_k[ia], cnt_k[ia]
+    att_flops = fl["attention"] * n_dw * args.steps
+    att_tf = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "attention_tc_kernel (tcgen05 QK^T / PV, softmax on MUFU)",
+                "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf,
+                "traffic": traffic_of("attention_tc_kernel"),
+                "algorithmic_bytes_per_launch": args.chunk * 1500 * (3 * d + d) * 2,
+                "peak_source": peak_src, "flops_per_launch": att_flops / max(att_n, 1),
+                "avg_launch_ms": att_ms / max(att_n, 1), "share_of_step": att_ms / max(sum(ms_k), 1e-9),
+                "note": "head_dim 64: 2 exp per 256 MAC -> MUFU.EX2 (16/clk/SM) needs 2x the tensor time of a tile; "
+                        "tensor-pipe ceiling of this kernel is ~50% of peak (profiles/r1_attention_ncu.txt)"}
     if "logmel" in kernels:
         lm_bytes = (2048 * 4 + 3002 * 80 * 2) * n_dw   # fused path writes bf16 time-major features
         kernels["logmel"]["gbs"] = lm_bytes / (kernels["logmel"]["ms_per_step"] * 1e-3) / 1e9
@@ -411,7 +437,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "strain-s/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": host_strain.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": int(launches_per_run), "host_issue_ms_per_step": host_issue_ms,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "roofline_gemm": roofline_gemm, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

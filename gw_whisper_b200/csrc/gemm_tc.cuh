@@ -68,18 +68,24 @@ constexpr int kGemmThreads = 384;   // 12 warps: TMA, MMA, TMEM alloc, spare, 8 
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 5 : 6);
+  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 4 : 6);
   static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 192;  // (2*stages+4) mbarriers + tmem ptr, stages <= 6
+  static constexpr int kStagingBytes = 8 * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
   // dynamic smem is declared __align__(1024); no slack needed (checked at kernel entry)
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes;
   // 227 KB opt-in limit minus the 1 KB the compiler reserves statically for the __align__(1024)
   static_assert(kTotal <= 232448 - 1024, "exceeds the dynamic shared memory limit of sm_100");
 };
 
-template <int BN, int EPI>
+// MC = 2: clusters of two CTAs work on vertically adjacent tiles (same n, m and m+1) in lockstep and
+// share the weight tile: each CTA fetches half of it and TMA-multicasts it into both, cutting the
+// L2 -> SM traffic per k-block from 48 KB to 32 KB (BN = 256).  With 128x256x64 stages the kernel moves
+// 1 byte per 85 FLOP, i.e. ~11.7 TB/s at 1 PFLOP/s -- the measured L2 ceiling (r1 ncu) -- so the
+// big-K GEMMs were L2-bound, not tensor-bound.
+template <int BN, int EPI, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
@@ -96,7 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __trap();
   }
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* staging_base = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + S::kStagingBytes);
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kStages;
@@ -110,8 +117,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_per_batch = (p.rows + 127) >> 7;
   const int tiles_m = tiles_per_batch * p.batch;
   const int tiles_n = (p.n + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.kb_per_tap * p.taps;
+  // work items: MC == 1 -> one tile per item; MC == 2 -> a vertical pair of tiles per cluster item
+  const uint32_t cta_rank = (MC > 1) ? cluster_ctarank() : 0u;
+  const int num_items = ((tiles_m + MC - 1) / MC) * tiles_n;
+  const int item0 = blockIdx.x / MC;
+  const int item_step = gridDim.x / MC;
+  auto item_to_tile = [&](int item, int& m_idx, int& n_idx) {
+    const int mp = item / tiles_n;
+    n_idx = item - mp * tiles_n;
+    m_idx = mp * MC + static_cast<int>(cta_rank);
+    return m_idx < tiles_m;       // false: this CTA only takes part in the pair's loads and barriers
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -120,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, MC);      // every CTA of the cluster releases a stage into all of them
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
@@ -134,6 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();   // peer barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -142,14 +160,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = tile / tiles_n;
-        const int n_idx = tile - m_idx * tiles_n;
+      for (int item = item0; item < num_items; item += item_step) {
+        int m_idx, n_idx;
+        const bool valid = item_to_tile(item, m_idx, n_idx);
         const int b = m_idx / tiles_per_batch;
         const int r0 = (m_idx - b * tiles_per_batch) << 7;
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
           // pull this tile's residual block into L2 one tile ahead of the epilogue that adds it
-          if (p.prefetch_resid) tma_prefetch_l2_2d(&tmR, n_idx * BN, b * p.rows + r0);
+          if (p.prefetch_resid && valid) tma_prefetch_l2_2d(&tmR, n_idx * BN, b * p.rows + r0);
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -158,8 +176,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
           const int tap = kb / p.kb_per_tap;
           const int kc = kb - tap * p.kb_per_tap;
-          tma_load_4d(sa, &tmA, full, kc * 64, tap % p.p_mod, r0 + tap / p.p_mod, b);
-          tma_load_2d(sa + S::kABytes, &tmB, full, kb * 64, n_idx * BN);
+          tma_load_4d(sa, &tmA, full, kc * 64, tap % p.p_mod, r0 + tap / p.p_mod, b);   // OOB (invalid tile): zeros
+          if constexpr (MC == 1) {
+            tma_load_2d(sa + S::kABytes, &tmB, full, kb * 64, n_idx * BN);
+          } else {
+            constexpr int HB = BN / MC;         // weight rows fetched by this CTA, multicast to the pair
+            tma_load_2d_mc(sa + S::kABytes + cta_rank * (HB * 128), &tmB, full, kb * 64,
+                           n_idx * BN + static_cast<int>(cta_rank) * HB, static_cast<uint16_t>((1u << MC) - 1u));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -171,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -186,7 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // +32 B per 16-element K step inside the 128B swizzle atom => +2 in the addr field
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);
+          if constexpr (MC == 1) umma_commit(bar_empty + 8 * stage);
+          else umma_commit_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << MC) - 1u));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(bar_tfull + 8 * as);
@@ -195,30 +220,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps: lane quarter = warp % 4, column half = (warp-4) / 4)
+    // tcgen05.ld hands every thread 32 consecutive columns of ITS row, so storing straight from the
+    // registers makes each warp-wide access touch 32 different 128-byte lines: the r1 ncu capture
+    // showed l1tex (tag lookups) as the busiest unit of every GEMM and the K=512 ones bound by it.
+    // Each warp therefore transposes its 32x32 chunk through a private swizzled smem buffer and moves
+    // whole 128-byte row segments per quarter-warp (4 lines per instruction instead of 32).
     const int e = warp - 4;
     const int q = e & 3;
     const int half = e >> 2;
     constexpr int HW = BN / 2;          // accumulator columns handled by one warp
+    constexpr int NC = HW / 32;         // 32-column chunks per warp
+    uint8_t* stg = staging_base + e * 4096;
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;          // this thread's row while staging
+    const int srow = lane >> 3, sslot = lane & 7;                 // (row-in-pass, 16-byte slot) while moving
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_idx = tile / tiles_n;
-      const int n_idx = tile - m_idx * tiles_n;
-      const int b = m_idx / tiles_per_batch;
-      const int r0 = (m_idx - b * tiles_per_batch) << 7;
+    for (int item = item0; item < num_items; item += item_step) {
+      int m_idx, n_idx;
+      const bool valid = item_to_tile(item, m_idx, n_idx);
+      const int b = valid ? m_idx / tiles_per_batch : 0;
+      const int r0 = valid ? (m_idx - b * tiles_per_batch) << 7 : 0;
       const int n0 = n_idx * BN + half * HW;
-      const int r = r0 + q * 32 + lane;       // this thread's output row inside the batch entry
-      const bool row_ok = r < p.rows;
-      const size_t c_off = static_cast<size_t>(b) * p.c_batch_stride +
-                           static_cast<size_t>(row_ok ? r : 0) * p.c_row_stride + n0;
+      const int rbase = r0 + q * 32;          // first row of this warp inside the batch entry
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * HW;
-      if constexpr (!kOutF32) {
-        constexpr int NC = HW / 32;         // 32-column chunks per warp
-        uint32_t v[2][32];
+      uint32_t v[2][32];
+      if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+        // GELU epilogues are issue-bound (measured: staging costs them 6 %): straight 256-bit stores
+        const int r = rbase + lane;
+        const bool row_ok = valid && r < p.rows;
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
+                              static_cast<size_t>(row_ok ? r : 0) * p.c_row_stride + n0;
         tmem_ld32(t_acc, v[0]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < NC) {
+            tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
+          } else {
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * as);
+          }
+          const int nc = n0 + c * 32;
+          if (nc < p.n) {
+            const uint32_t(&vc)[32] = v[c & 1];
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = (p.bias != nullptr) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float a0 = gelu_erf_fast(__uint_as_float(vc[4 * j]) + bv.x);
+              const float a1 = gelu_erf_fast(__uint_as_float(vc[4 * j + 1]) + bv.y);
+              const float a2 = gelu_erf_fast(__uint_as_float(vc[4 * j + 2]) + bv.z);
+              const float a3 = gelu_erf_fast(__uint_as_float(vc[4 * j + 3]) + bv.w);
+              pk[2 * j] = pack_bf16x2(a0, a1);
+              pk[2 * j + 1] = pack_bf16x2(a2, a3);
+            }
+            if (row_ok) {
+              uint32_t lo[8], hi[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
+              st_global_v8(crow + c * 32, lo);
+              st_global_v8(crow + c * 32 + 16, hi);
+            }
+          }
+        }
+      } else if constexpr (!kOutF32) {
+        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride + n0;
+        // move `ncols` (32 or 64) staged bf16 columns starting at column `col0` of the warp's range
+        auto flush = [&](int col0, int ncols) {
+          __syncwarp();
+          if (ncols == 64) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              const int row = 4 * ps + srow;
+              const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
+              const int rr = rbase + row;
+              if (valid && rr < p.rows)
+                *reinterpret_cast<uint4*>(cb + static_cast<size_t>(rr) * p.c_row_stride + col0 + 8 * sslot) = d;
+            }
+          } else {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int row = 8 * ps + (lane >> 2), sl = lane & 3;
+              const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sl ^ (row & 7)) << 4));
+              const int rr = rbase + row;
+              if (valid && rr < p.rows)
+                *reinterpret_cast<uint4*>(cb + static_cast<size_t>(rr) * p.c_row_stride + col0 + 8 * sl) = d;
+            }
+          }
+          __syncwarp();
+        };
+        tmem_ld32(t_acc, v[0]);
+        int pending = 0;                      // staged, not yet flushed columns
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           tmem_wait_ld();
@@ -232,84 +328,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nc < p.n) {                          // (N is a multiple of 64: chunk fully in or out)
             const uint32_t(&vc)[32] = v[c & 1];
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
-            uint32_t pk[16];
+            const int hslot = (pending == 32) ? 4 : 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bv = (p.bias != nullptr) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float a0 = __uint_as_float(vc[4 * j]) + bv.x, a1 = __uint_as_float(vc[4 * j + 1]) + bv.y;
-              float a2 = __uint_as_float(vc[4 * j + 2]) + bv.z, a3 = __uint_as_float(vc[4 * j + 3]) + bv.w;
-              if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-                a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
-                a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
+            for (int j = 0; j < 4; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 bv = (p.bias != nullptr) ? __ldg(b4 + 2 * j + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bv.x, a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bv.y;
+                float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bv.z, a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bv.w;
+                if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                  a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
+                  a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
+                }
+                pk[2 * h] = pack_bf16x2(a0, a1);
+                pk[2 * h + 1] = pack_bf16x2(a2, a3);
               }
-              pk[2 * j] = pack_bf16x2(a0, a1);
-              pk[2 * j + 1] = pack_bf16x2(a2, a3);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_row + (((hslot + j) ^ (lane & 7)) << 4)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
             }
-            if (row_ok) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + c_off + c * 32;
-              uint32_t lo[8], hi[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
-              st_global_v8(dst, lo);
-              st_global_v8(dst + 16, hi);
-            }
+            pending += 32;
+            if (pending == 64) { flush(c * 32 - 32, 64); pending = 0; }
           }
+          if (c + 1 == NC && pending == 32) { flush(c * 32 - (nc < p.n ? 0 : 32), 32); pending = 0; }
         }
       } else {
-        constexpr int NS = HW / 16;         // 16-column steps per warp
-        uint32_t v[2][16];
-        uint32_t add[2][16];
-        const float* addp;                  // residual / positional row segment of this thread
-        if constexpr (EPI == EPI_BIAS_RESID_F32)
-          addp = p.resid + (static_cast<size_t>(b) * p.rows + (row_ok ? r : 0)) * p.n + n0;
-        else
-          addp = p.pos + static_cast<size_t>(row_ok ? r : 0) * p.n + n0;
-        auto load_add = [&](int s, uint32_t (&dst)[16]) {
-          uint32_t t8[8];
-          ld_global_v8(addp + 16 * s, t8);
+        // residual / positional addend: fetched in the MOVE layout (coalesced), one chunk ahead
+        const float* addb;
+        if constexpr (EPI == EPI_BIAS_RESID_F32) addb = p.resid + static_cast<size_t>(b) * p.rows * p.n + n0;
+        else addb = p.pos + n0;
+        float* cb = reinterpret_cast<float*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride + n0;
+        float4 add[2][8];
+        auto load_add = [&](int c, float4 (&dst)[8]) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = t8[i];
-          ld_global_v8(addp + 16 * s + 8, t8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dst[8 + i] = t8[i];
+          for (int ps = 0; ps < 8; ++ps) {
+            const int rr = rbase + 4 * ps + srow;
+            dst[ps] = (valid && rr < p.rows)
+                          ? *reinterpret_cast<const float4*>(addb + static_cast<size_t>(rr) * p.n + c * 32 + 4 * sslot)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         };
-        tmem_ld16(t_acc, v[0]);
+        tmem_ld32(t_acc, v[0]);
         load_add(0, add[0]);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
+        for (int c = 0; c < NC; ++c) {
           tmem_wait_ld();
-          if (s + 1 < NS) {
-            tmem_ld16(t_acc + (s + 1) * 16, v[(s + 1) & 1]);
-            load_add(s + 1, add[(s + 1) & 1]);
+          if (c + 1 < NC) {
+            tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
+            load_add(c + 1, add[(c + 1) & 1]);
           } else {
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * as);
           }
-          const uint32_t(&vc)[16] = v[s & 1];
-          const uint32_t(&ac)[16] = add[s & 1];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 16);
-          float* dst = reinterpret_cast<float*>(p.c) + c_off + s * 16;
+          const uint32_t(&vc)[32] = v[c & 1];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint32_t o[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 bv = (p.bias != nullptr) ? __ldg(b4 + 2 * j + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bv.x;
-              float a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bv.y;
-              float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bv.z;
-              float a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bv.w;
-              if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-                a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
-                a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
-              }
-              o[4 * h] = __float_as_uint(a0 + __uint_as_float(ac[8 * j + 4 * h]));
-              o[4 * h + 1] = __float_as_uint(a1 + __uint_as_float(ac[8 * j + 4 * h + 1]));
-              o[4 * h + 2] = __float_as_uint(a2 + __uint_as_float(ac[8 * j + 4 * h + 2]));
-              o[4 * h + 3] = __float_as_uint(a3 + __uint_as_float(ac[8 * j + 4 * h + 3]));
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = (p.bias != nullptr) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float a0 = __uint_as_float(vc[4 * j]) + bv.x, a1 = __uint_as_float(vc[4 * j + 1]) + bv.y;
+            float a2 = __uint_as_float(vc[4 * j + 2]) + bv.z, a3 = __uint_as_float(vc[4 * j + 3]) + bv.w;
+            if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+              a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
+              a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
             }
-            if (row_ok) st_global_v8(dst + 8 * j, o);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stg_row + ((j ^ (lane & 7)) << 4)),
+                         "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
           }
+          __syncwarp();
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps) {
+            const int row = 4 * ps + srow;
+            float4 d = *reinterpret_cast<const float4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
+            const float4 ad = add[c & 1][ps];
+            d.x += ad.x; d.y += ad.y; d.z += ad.z; d.w += ad.w;
+            const int rr = rbase + row;
+            if (valid && rr < p.rows)
+              *reinterpret_cast<float4*>(cb + static_cast<size_t>(rr) * p.c_row_stride + c * 32 + 4 * sslot) = d;
+          }
+          __syncwarp();
         }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
@@ -318,6 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);

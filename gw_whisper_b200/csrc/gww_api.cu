@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -82,11 +83,12 @@ extern "C" int gww_device_ok(void) {
 // ------------------------------------------------------------------------------------------------
 enum ProfKind : int {
   PK_LOGMEL = 0, PK_FEATS_TM, PK_GEMM_CONV1, PK_GEMM_CONV2, PK_LN, PK_GEMM_QKV, PK_ATTN, PK_GEMM_O,
-  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_COUNT
+  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_ATTN_LAST, PK_COUNT
 };
 static const char* kProfNames[PK_COUNT] = {"logmel", "feats_to_timemajor", "gemm_conv1", "gemm_conv2",
                                            "layernorm", "gemm_qkv", "attention", "gemm_out_proj",
-                                           "gemm_fc1", "gemm_fc2", "head", "other", "qscan", "qadapter"};
+                                           "gemm_fc1", "gemm_fc2", "head", "other", "qscan", "qadapter",
+                                           "attention_last_row"};
 struct ProfRec { cudaEvent_t a, b; int kind; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof_recs;
@@ -232,33 +234,63 @@ struct GemmCall {
   int kind = PK_OTHER;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MC>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR,
                          const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, EPI>;
+  auto kern = gemm_tc_kernel<BN, EPI, MC>;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 GemmSmem<BN>::kTotal));
     attr_set = true;
   }
-  const int tiles = ((p.rows + 127) / 128) * p.batch * ((p.n + BN - 1) / BN);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, tmR, p);
+  const int tiles_m = ((p.rows + 127) / 128) * p.batch;
+  const int items = ((tiles_m + MC - 1) / MC) * ((p.n + BN - 1) / BN);
+  const int max_groups = g_num_sms / MC;
+  const int grid = (items < max_groups ? items : max_groups) * MC;
+  if constexpr (MC == 1) {
+    kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, tmR, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = MC;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CU_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmR, p));
+  }
   LAUNCH_CHECK();
   return GWW_OK;
 }
 
-template <int BN>
+template <int BN, int MC>
 static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& r,
                           const GemmParams& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16>(a, b, r, p, s);
-    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16>(a, b, r, p, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32>(a, b, r, p, s);
-    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32>(a, b, r, p, s);
+    case EPI_BIAS_BF16: return launch_gemm_t<BN, EPI_BIAS_BF16, MC>(a, b, r, p, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_t<BN, EPI_BIAS_GELU_BF16, MC>(a, b, r, p, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm_t<BN, EPI_BIAS_RESID_F32, MC>(a, b, r, p, s);
+    case EPI_BIAS_GELU_POS_F32: return launch_gemm_t<BN, EPI_BIAS_GELU_POS_F32, MC>(a, b, r, p, s);
   }
   return fail(GWW_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
+// 2-CTA weight multicast pays off once there are enough tile pairs to keep every SM pair busy
+static int gemm_multicast(const GemmParams& p) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("GWW_GEMM_MC");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2) return forced;
+  const int tiles_m = ((p.rows + 127) / 128) * p.batch;
+  return tiles_m >= g_num_sms ? 2 : 1;
 }
 
 static int run_gemm(const GemmCall& g, cudaStream_t stream) {
@@ -272,7 +304,8 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   GWW_TRY(make_map(&tmA, false, 4, g.a_base, g.a_dims, g.a_strides, abox));
   const uint64_t wdims[2] = {(uint64_t)g.ktot, (uint64_t)g.p.n};
   const uint64_t wstr[1] = {(uint64_t)g.ktot * 2};
-  const uint32_t wbox[2] = {64, (uint32_t)g.block_n};
+  const int mc = gemm_multicast(g.p);
+  const uint32_t wbox[2] = {64, (uint32_t)(g.block_n / mc)};
   GWW_TRY(make_map(&tmB, false, 2, g.w_base, wdims, wstr, wbox));
   GemmParams p = g.p;
   const uint64_t esz = out_f32 ? 4 : 2;
@@ -292,10 +325,13 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
     p.prefetch_resid = 1;
   }
   ProfScope ps(g.kind, stream);
-  switch (g.block_n) {
-    case 128: return launch_gemm_bn<128>(g.epi, tmA, tmB, tmR, p, stream);
-    case 192: return launch_gemm_bn<192>(g.epi, tmA, tmB, tmR, p, stream);
-    case 256: return launch_gemm_bn<256>(g.epi, tmA, tmB, tmR, p, stream);
+  switch (g.block_n * 10 + mc) {
+    case 1281: return launch_gemm_bn<128, 1>(g.epi, tmA, tmB, tmR, p, stream);
+    case 1921: return launch_gemm_bn<192, 1>(g.epi, tmA, tmB, tmR, p, stream);
+    case 2561: return launch_gemm_bn<256, 1>(g.epi, tmA, tmB, tmR, p, stream);
+    case 1282: return launch_gemm_bn<128, 2>(g.epi, tmA, tmB, tmR, p, stream);
+    case 1922: return launch_gemm_bn<192, 2>(g.epi, tmA, tmB, tmR, p, stream);
+    case 2562: return launch_gemm_bn<256, 2>(g.epi, tmA, tmB, tmR, p, stream);
   }
   return fail(GWW_ERR_INVALID, "gemm: block_n must be 128, 192 or 256 (got %d)", g.block_n);
 }
@@ -731,7 +767,7 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
       GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
       GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
       {
-        ProfScope ps(PK_ATTN, stream);
+        ProfScope ps(PK_ATTN_LAST, stream);
         const size_t smem = (size_t)(((T + 3) & ~3) + 8 * 64 + 16) * sizeof(float);
         last_row_attention_kernel<<<dim3(d / 64, nc), 256, smem, stream>>>(qkv, hl, T, d);
         LAUNCH_CHECK();
