@@ -78,7 +78,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
   const uint32_t bar_pvdone = bar_sfree + 16;               // 2 (mma -> softmax: P.V finished)
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 1 + 4 * kAttnStages + 10);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int wg = warp >> 2;
   const int qpair = blockIdx.x, head = blockIdx.y, bi = blockIdx.z;
@@ -115,59 +115,72 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
 
   if (wg == 2) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    if (warp == 8 && lane == 0) {
+    // Both single-thread roles are written as warp-uniform loops in which one elected lane issues the
+    // TMA / tcgen05 instructions (see elect_one() in ptx.cuh): the r1 profile showed the lone MMA
+    // thread of the `lane == 0` version busy ~90 % of the time executing ~360 instructions per key
+    // tile, i.e. Q.K^T and P.V were issued late and both softmax groups waited for them.
+    if (warp == 8) {
       // ===================== TMA producer =====================
-      mbar_arrive_expect_tx(bar_q, 32768);
-      tma_load_3d(smem_u32(q_s), &tmQKV, bar_q, head * 64, q0, bi);
-      tma_load_3d(smem_u32(q_s + 16384), &tmQKV, bar_q, head * 64, q0 + 128, bi);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q, 32768);
+        tma_load_3d(smem_u32(q_s), &tmQKV, bar_q, head * 64, q0, bi);
+        tma_load_3d(smem_u32(q_s + 16384), &tmQKV, bar_q, head * 64, q0 + 128, bi);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t k_smem = smem_u32(k_s), v_smem = smem_u32(v_s);
+      const int kcol = p.d_model + head * 64, vcol = 2 * p.d_model + head * 64;
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(bar_kempty + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(bar_kfull + 8 * stage, 16384);
-        tma_load_3d(smem_u32(k_s + stage * 16384), &tmQKV, bar_kfull + 8 * stage,
-                    p.d_model + head * 64, j * 128, bi);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_kfull + 8 * stage, 16384);
+          tma_load_3d(k_smem + stage * 16384, &tmQKV, bar_kfull + 8 * stage, kcol, j * 128, bi);
+        }
+        __syncwarp();
         mbar_wait(bar_vempty + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(bar_vfull + 8 * stage, 16384);
-        tma_load_3d(smem_u32(v_s + stage * 16384), &tmQKV, bar_vfull + 8 * stage,
-                    2 * p.d_model + head * 64, j * 128, bi);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_vfull + 8 * stage, 16384);
+          tma_load_3d(v_smem + stage * 16384, &tmQKV, bar_vfull + 8 * stage, vcol, j * 128, bi);
+        }
+        __syncwarp();
         if (++stage == kAttnStages) { stage = 0; phase ^= 1; }
       }
-    } else if (warp == 9 && lane == 0) {
+    } else if (warp == 9) {
       // ===================== MMA issuer =====================
       constexpr uint32_t kIdescS = make_idesc_bf16(128, 128, 0);
       constexpr uint32_t kIdescO = make_idesc_bf16(128, 64, 1);   // V is MN-major
-      const uint32_t tS[2] = {tmem_base + 0u, tmem_base + 128u};
-      const uint32_t tP[2] = {tmem_base + 256u, tmem_base + 320u};
-      const uint32_t tO[2] = {tmem_base + 384u, tmem_base + 448u};
-      const uint64_t qdesc[2] = {make_sw128_desc(smem_u32(q_s)),
-                                 make_sw128_desc(smem_u32(q_s + 16384))};
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_kfull, 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = make_sw128_desc(smem_u32(k_s));
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
-          umma_commit(bar_sfull + 8 * t);
-        }
-        umma_commit(bar_kempty);
-      }
-      // issue order per step j:  S0(j+1) | P1(j-1).V | S1(j+1) | P0(j).V   (matches the order in
-      // which the staggered softmax groups produce their events; any other order is still safe)
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
+      const uint32_t tS[2] = {tb + 0u, tb + 128u};
+      const uint32_t tP[2] = {tb + 256u, tb + 320u};
+      const uint32_t tO[2] = {tb + 384u, tb + 448u};
+      const uint32_t q_smem = smem_u32(q_s), k_smem = smem_u32(k_s), v_smem = smem_u32(v_s);
+      const uint64_t qdesc[2] = {make_sw128_desc(q_smem), make_sw128_desc(q_smem + 16384)};
+      // S_t = Q_t K^T (4 MMAs of K=16) and its commit
       auto issue_s = [&](int t, const uint64_t kdesc) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tS[t], qdesc[t] + 2 * k, kdesc + 2 * k, kIdescS, k);
         umma_commit(bar_sfull + 8 * t);
       };
+      // O_t (+)= P_t V (8 MMAs of K=16 keys) and its commit
       auto issue_pv = [&](int t, const uint64_t vdesc, bool first) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ts(tO[t], tP[t] + 8 * k, vdesc + 128 * k, kIdescO, (!first || k) ? 1u : 0u);
         umma_commit(bar_pvdone + 8 * t);
       };
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kfull, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t kdesc = make_sw128_desc(k_smem);
+        issue_s(0, kdesc);
+        issue_s(1, kdesc);
+        umma_commit(bar_kempty);
+      }
+      __syncwarp();
+      // issue order per step j:  S0(j+1) | P1(j-1).V | S1(j+1) | P0(j).V   (matches the order in
+      // which the softmax groups produce their events; any other order is still safe)
       int stage = 0;              // stage of K/V tile j
       uint32_t phase = 0;
       int pstage = 0;             // stage of V tile j-1
@@ -176,39 +189,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
         uint32_t nphase = phase;
         if (nstage == kAttnStages) { nstage = 0; nphase ^= 1; }
         const bool has_next = (j + 1 < nkv);
-        const uint64_t kdesc_n = make_sw128_desc(smem_u32(k_s + nstage * 16384));
+        const uint64_t kdesc_n = make_sw128_desc(k_smem + nstage * 16384);
         if (has_next) {
           mbar_wait(bar_kfull + 8 * nstage, nphase);
           mbar_wait(bar_sfree + 8 * 0, j & 1);
           tc_fence_after();
-          issue_s(0, kdesc_n);
+          if (elect_one()) issue_s(0, kdesc_n);
+          __syncwarp();
         }
         if (j >= 1) {
           mbar_wait(bar_pfull + 8 * 1, (j - 1) & 1);
           tc_fence_after();
-          issue_pv(1, make_sw128_desc(smem_u32(v_s + pstage * 16384)), j - 1 == 0);
-          umma_commit(bar_vempty + 8 * pstage);
+          if (elect_one()) {
+            issue_pv(1, make_sw128_desc(v_smem + pstage * 16384), j - 1 == 0);
+            umma_commit(bar_vempty + 8 * pstage);
+          }
+          __syncwarp();
         }
         if (has_next) {
           mbar_wait(bar_sfree + 8 * 1, j & 1);
           tc_fence_after();
-          issue_s(1, kdesc_n);
-          umma_commit(bar_kempty + 8 * nstage);
+          if (elect_one()) {
+            issue_s(1, kdesc_n);
+            umma_commit(bar_kempty + 8 * nstage);
+          }
+          __syncwarp();
         }
         mbar_wait(bar_vfull + 8 * stage, phase);
         mbar_wait(bar_pfull + 8 * 0, j & 1);
         tc_fence_after();
-        issue_pv(0, make_sw128_desc(smem_u32(v_s + stage * 16384)), j == 0);
-        if (!has_next) umma_commit(bar_ofull + 8 * 0);
+        if (elect_one()) {
+          issue_pv(0, make_sw128_desc(v_smem + stage * 16384), j == 0);
+          if (!has_next) umma_commit(bar_ofull + 8 * 0);
+        }
+        __syncwarp();
         pstage = stage;
         stage = nstage;
         phase = nphase;
       }
       mbar_wait(bar_pfull + 8 * 1, (nkv - 1) & 1);
       tc_fence_after();
-      issue_pv(1, make_sw128_desc(smem_u32(v_s + pstage * 16384)), nkv - 1 == 0);
-      umma_commit(bar_vempty + 8 * pstage);
-      umma_commit(bar_ofull + 8 * 1);
+      if (elect_one()) {
+        issue_pv(1, make_sw128_desc(v_smem + pstage * 16384), nkv - 1 == 0);
+        umma_commit(bar_vempty + 8 * pstage);
+        umma_commit(bar_ofull + 8 * 1);
+      }
+      __syncwarp();
     }
   } else {
     // ===================== softmax warpgroups =====================

@@ -49,7 +49,18 @@ struct GemmParams {
   const float* resid;  // [batch*rows, n] f32 (EPI_BIAS_RESID_F32)
   const float* pos;    // [rows, n] f32 (EPI_BIAS_GELU_POS_F32)
   int prefetch_resid;  // tmR is a valid {n, batch*rows} f32 map of resid: L2-prefetch it per tile
+  // filled by the launcher: floor(2^40 / d) + 1 for d = tiles_n and d = tiles_per_batch (exact x / d for
+  // x < 2^24, d < 2^16) -- the per-tile index math must not cost integer divisions in the single-thread loops
+  unsigned long long magic_tiles_n;
+  unsigned long long magic_tiles_per_batch;
 };
+
+__host__ __device__ __forceinline__ unsigned long long gemm_div_magic(int d) {
+  return ((1ull << 40) / static_cast<unsigned long long>(d)) + 1ull;
+}
+__device__ __forceinline__ int gemm_fast_div(int x, unsigned long long magic) {
+  return static_cast<int>((static_cast<unsigned long long>(x) * magic) >> 40);
+}
 
 // erf-GELU (HF ACT2FN["gelu"], modeling_whisper.py:403) in 8 instructions + 1 MUFU:
 //   gelu(v) = 0.5 v (1 + erf(v/sqrt2)) ~= 0.5 v (1 + tanh(v (c1 + c2 v^2 + c3 v^4)))
@@ -66,34 +77,44 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
 
 constexpr int kGemmThreads = 384;   // 12 warps: TMA, MMA, TMEM alloc, spare, 8 x epilogue
 
-template <int BN>
+template <int BN, int MC = 1>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 192) ? 4 : 6);
+  // MC == 2 (CTA pair): each CTA stages only its half of the weight tile
   static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBBytes = (BN / MC) * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 192;  // (2*stages+4) mbarriers + tmem ptr, stages <= 6
   static constexpr int kStagingBytes = 8 * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
+  static constexpr int kBiasFloats = 3072;         // the whole bias vector lives in smem (N <= 3072)
+  static constexpr int kBiasBytes = kBiasFloats * 4;
+  static constexpr int kLimit = 232448 - 1024;     // 227 KB opt-in minus the 1 KB reserved for __align__(1024)
+  static constexpr int kFit = (kLimit - kStagingBytes - kBiasBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 6 ? 6 : kFit;
+  static_assert(kStages >= 3, "too few pipeline stages");
   // dynamic smem is declared __align__(1024); no slack needed (checked at kernel entry)
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes;
-  // 227 KB opt-in limit minus the 1 KB the compiler reserves statically for the __align__(1024)
-  static_assert(kTotal <= 232448 - 1024, "exceeds the dynamic shared memory limit of sm_100");
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes;
+  static_assert(kTotal <= kLimit, "exceeds the dynamic shared memory limit of sm_100");
 };
 
-// MC = 2: clusters of two CTAs work on vertically adjacent tiles (same n, m and m+1) in lockstep and
-// share the weight tile: each CTA fetches half of it and TMA-multicasts it into both, cutting the
-// L2 -> SM traffic per k-block from 48 KB to 32 KB (BN = 256).  With 128x256x64 stages the kernel moves
-// 1 byte per 85 FLOP, i.e. ~11.7 TB/s at 1 PFLOP/s -- the measured L2 ceiling (r1 ncu) -- so the
-// big-K GEMMs were L2-bound, not tensor-bound.
+// MC = 2: a CTA pair (cluster of two, the two SMs of a TPC) computes a 256 x BN tile with ONE
+// tcgen05.mma.cta_group::2 stream issued by the leader (cluster rank 0): CTA r owns rows [128r, 128r+128)
+// of the tile (its A rows in its smem, its accumulator rows in its TMEM) and stages only weight rows
+// [r*BN/2, (r+1)*BN/2) -- the tensor core reads the other half from the peer's shared memory.  With
+// 128x256x64 single-CTA stages every SM ingests 48 KB per 512 tensor clocks (1 byte per 85 FLOP,
+// ~12-13 TB/s of L2 -> SM traffic at 1 PFLOP/s: the measured crossbar ceiling, r1 ncu
+// l1tex__m_xbar2l1tex_read_bytes), so the K >= 512 GEMMs were fabric-bound at ~60 % tensor-active; the
+// pair needs 32 KB per SM for the same math.  (A TMA-multicast variant was measured first: no gain,
+// since multicast saves L2 reads but not per-SM ingest.)
 template <int BN, int EPI, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, MC>;
   constexpr int kStages = S::kStages;
   constexpr bool kOutF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
   constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0);
+  constexpr uint32_t kIdesc = make_idesc_bf16(128 * MC, BN, 0);
+  constexpr uint16_t kPairMask = 0x3;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -103,7 +124,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   uint8_t* stage_base = smem;
   uint8_t* staging_base = smem + kStages * S::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + S::kStagingBytes);
+  float* bias_s = reinterpret_cast<float*>(staging_base + S::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + S::kStagingBytes + S::kBiasBytes);
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kStages;
@@ -111,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_tempty = bar_tfull + 16;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   const int tiles_per_batch = (p.rows + 127) >> 7;
@@ -124,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int item0 = blockIdx.x / MC;
   const int item_step = gridDim.x / MC;
   auto item_to_tile = [&](int item, int& m_idx, int& n_idx) {
-    const int mp = item / tiles_n;
+    const int mp = gemm_fast_div(item, p.magic_tiles_n);
     n_idx = item - mp * tiles_n;
     m_idx = mp * MC + static_cast<int>(cta_rank);
     return m_idx < tiles_m;       // false: this CTA only takes part in the pair's loads and barriers
@@ -134,87 +156,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
+  // the bias vector is read by every epilogue thread for every tile: keep it in shared memory (the r1
+  // profile showed the per-chunk global bias loads missing L1 and stalling each chunk ~500 clocks)
+  for (int i = threadIdx.x; i < p.n; i += kGemmThreads) bias_s[i] = (p.bias != nullptr) ? p.bias[i] : 0.0f;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, MC);      // every CTA of the cluster releases a stage into all of them
+      mbar_init(bar_empty + 8 * i, 1);       // pair: the leader's commit is multicast into both CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 256);
+      mbar_init(bar_tempty + 8 * i, MC == 1 ? 256 : 16);   // pair: one arrival per epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<kTmemCols>(smem_u32(tmem_ptr_s));
-    tmem_relinquish();
+    if constexpr (MC == 1) {
+      tmem_alloc<kTmemCols>(smem_u32(tmem_ptr_s));
+      tmem_relinquish();
+    } else {
+      tmem_alloc_pair<kTmemCols>(smem_u32(tmem_ptr_s));   // same warp, same smem offset in both CTAs
+      tmem_relinquish_pair();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC > 1) cluster_sync_all();   // peer barriers exist before anything is multicast at them
+  if constexpr (MC > 1) cluster_sync_all();   // peer barriers exist before anything arrives at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t full_leader = (MC > 1) ? mapa_cluster(bar_full, 0) : bar_full;
+      const uint32_t stage_smem = smem_u32(stage_base);
       for (int item = item0; item < num_items; item += item_step) {
         int m_idx, n_idx;
         const bool valid = item_to_tile(item, m_idx, n_idx);
-        const int b = m_idx / tiles_per_batch;
+        const int b = gemm_fast_div(m_idx, p.magic_tiles_per_batch);
         const int r0 = (m_idx - b * tiles_per_batch) << 7;
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
           // pull this tile's residual block into L2 one tile ahead of the epilogue that adds it
-          if (p.prefetch_resid && valid) tma_prefetch_l2_2d(&tmR, n_idx * BN, b * p.rows + r0);
+          if (p.prefetch_resid && valid && elect_one()) tma_prefetch_l2_2d(&tmR, n_idx * BN, b * p.rows + r0);
+          __syncwarp();
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, S::kStageBytes);
-          const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
-          const int tap = kb / p.kb_per_tap;
-          const int kc = kb - tap * p.kb_per_tap;
-          tma_load_4d(sa, &tmA, full, kc * 64, tap % p.p_mod, r0 + tap / p.p_mod, b);   // OOB (invalid tile): zeros
-          if constexpr (MC == 1) {
-            tma_load_2d(sa + S::kABytes, &tmB, full, kb * 64, n_idx * BN);
-          } else {
-            constexpr int HB = BN / MC;         // weight rows fetched by this CTA, multicast to the pair
-            tma_load_2d_mc(sa + S::kABytes + cta_rank * (HB * 128), &tmB, full, kb * 64,
-                           n_idx * BN + static_cast<int>(cta_rank) * HB, static_cast<uint16_t>((1u << MC) - 1u));
+        // (no integer divisions in this loop: a single thread issues it and must stay well ahead of
+        //  the 512 tensor clocks one k-block lasts)
+        const int n_row = n_idx * BN + ((MC > 1) ? static_cast<int>(cta_rank) * (BN / MC) : 0);
+        int tap_p = 0, tap_r = r0, kcol = 0;       // (tap % P, r0 + tap / P), weight column of the k-block
+        for (int tap = 0; tap < p.taps; ++tap) {
+          for (int kc = 0; kc < p.kb_per_tap; ++kc, kcol += 64) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t full = bar_full + 8 * stage;
+            const uint32_t sa = stage_smem + stage * S::kStageBytes;
+            if (elect_one()) {
+              if constexpr (MC == 1) {
+                mbar_arrive_expect_tx(full, S::kStageBytes);
+                tma_load_4d(sa, &tmA, full, kc * 64, tap_p, tap_r, b);
+                tma_load_2d(sa + S::kABytes, &tmB, full, kcol, n_row);
+              } else {
+                // both CTAs' boxes complete on the LEADER's full barrier, which expects the bytes of both
+                if (cta_rank == 0) mbar_arrive_expect_tx(full, MC * S::kStageBytes);
+                const uint32_t lfull = full_leader + 8 * stage;
+                tma_load_4d_pair(sa, &tmA, lfull, kc * 64, tap_p, tap_r, b);   // OOB (invalid tile): zeros
+                tma_load_2d_pair(sa + S::kABytes, &tmB, lfull, kcol, n_row);
+              }
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++tap_p == p.p_mod) { tap_p = 0; ++tap_r; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+    // warp-uniform loop; the elected lane issues the MMAs and commits
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const uint32_t stage_smem = smem_u32(stage_base);
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
       for (int item = item0; item < num_items; item += item_step) {
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base_u + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
+          const uint32_t sa = stage_smem + stage * S::kStageBytes;
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + S::kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 B per 16-element K step inside the 128B swizzle atom => +2 in the addr field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // +32 B per 16-element K step inside the 128B swizzle atom => +2 in the addr field
+              if constexpr (MC == 1) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+              else umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+            }
+            if constexpr (MC == 1) umma_commit(bar_empty + 8 * stage);
+            else umma_commit_pair(bar_empty + 8 * stage, kPairMask);   // frees the stage in both CTAs
+            if (kb + 1 == num_kb) {
+              if constexpr (MC == 1) umma_commit(bar_tfull + 8 * as);
+              else umma_commit_pair(bar_tfull + 8 * as, kPairMask);    // accumulator halves ready in both CTAs
+            }
           }
-          if constexpr (MC == 1) umma_commit(bar_empty + 8 * stage);
-          else umma_commit_mc(bar_empty + 8 * stage, static_cast<uint16_t>((1u << MC) - 1u));
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * as);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -235,13 +288,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int srow = lane >> 3, sslot = lane & 7;                 // (row-in-pass, 16-byte slot) while moving
     int as = 0;
     uint32_t aphase = 0;
+    const uint32_t tempty_leader = (MC > 1) ? mapa_cluster(bar_tempty, 0) : bar_tempty;
+    // all of this thread's tcgen05.ld of accumulator `a` have completed (tcgen05.wait::ld precedes)
+    auto release_acc = [&](int a) {
+      tc_fence_before();
+      if constexpr (MC == 1) {
+        mbar_arrive(bar_tempty + 8 * a);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * a);
+      }
+    };
     for (int item = item0; item < num_items; item += item_step) {
       int m_idx, n_idx;
       const bool valid = item_to_tile(item, m_idx, n_idx);
-      const int b = valid ? m_idx / tiles_per_batch : 0;
+      const int b = valid ? gemm_fast_div(m_idx, p.magic_tiles_per_batch) : 0;
       const int r0 = valid ? (m_idx - b * tiles_per_batch) << 7 : 0;
       const int n0 = n_idx * BN + half * HW;
       const int rbase = r0 + q * 32;          // first row of this warp inside the batch entry
+      const int rows_here = valid ? (p.rows - rbase) : 0;   // rows [0, rows_here) of this warp's 32 exist
+      const float* bias_w = bias_s + n0;      // this warp's bias slice (may run past N for a ragged last tile)
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
@@ -249,32 +315,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t v[2][32];
       if constexpr (EPI == EPI_BIAS_GELU_BF16) {
         // GELU epilogues are issue-bound (measured: staging costs them 6 %): straight 256-bit stores
-        const int r = rbase + lane;
-        const bool row_ok = valid && r < p.rows;
+        const bool row_ok = lane < rows_here;
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
-                              static_cast<size_t>(row_ok ? r : 0) * p.c_row_stride + n0;
+                              static_cast<size_t>(row_ok ? rbase + lane : 0) * p.c_row_stride + n0;
         tmem_ld32(t_acc, v[0]);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
+          const int nc = n0 + c * 32;
+          float4 bv[8];
+          if (nc < p.n) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+          }
           tmem_wait_ld();
           if (c + 1 < NC) {
             tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
           } else {
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);
+            release_acc(as);
           }
-          const int nc = n0 + c * 32;
           if (nc < p.n) {
             const uint32_t(&vc)[32] = v[c & 1];
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 bv = (p.bias != nullptr) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float a0 = gelu_erf_fast(__uint_as_float(vc[4 * j]) + bv.x);
-              const float a1 = gelu_erf_fast(__uint_as_float(vc[4 * j + 1]) + bv.y);
-              const float a2 = gelu_erf_fast(__uint_as_float(vc[4 * j + 2]) + bv.z);
-              const float a3 = gelu_erf_fast(__uint_as_float(vc[4 * j + 3]) + bv.w);
+              const float a0 = gelu_erf_fast(__uint_as_float(vc[4 * j]) + bv[j].x);
+              const float a1 = gelu_erf_fast(__uint_as_float(vc[4 * j + 1]) + bv[j].y);
+              const float a2 = gelu_erf_fast(__uint_as_float(vc[4 * j + 2]) + bv[j].z);
+              const float a3 = gelu_erf_fast(__uint_as_float(vc[4 * j + 3]) + bv[j].w);
               pk[2 * j] = pack_bf16x2(a0, a1);
               pk[2 * j + 1] = pack_bf16x2(a2, a3);
             }
@@ -288,27 +355,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else if constexpr (!kOutF32) {
-        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride + n0;
-        // move `ncols` (32 or 64) staged bf16 columns starting at column `col0` of the warp's range
+        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
+                            static_cast<size_t>(rbase) * p.c_row_stride + n0;
+        // move `ncols` (32 or 64) staged bf16 columns starting at column `col0` of the warp's range:
+        // all shared loads first, then the stores (independent registers: the accesses overlap)
         auto flush = [&](int col0, int ncols) {
           __syncwarp();
           if (ncols == 64) {
+            uint4 d[8];
 #pragma unroll
             for (int ps = 0; ps < 8; ++ps) {
               const int row = 4 * ps + srow;
-              const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
-              const int rr = rbase + row;
-              if (valid && rr < p.rows)
-                *reinterpret_cast<uint4*>(cb + static_cast<size_t>(rr) * p.c_row_stride + col0 + 8 * sslot) = d;
+              d[ps] = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
+            }
+            __nv_bfloat16* dst = cb + static_cast<size_t>(srow) * p.c_row_stride + col0 + 8 * sslot;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+              if (4 * ps + srow < rows_here) *reinterpret_cast<uint4*>(dst) = d[ps];
+              dst += 4 * p.c_row_stride;
             }
           } else {
+            const int sl = lane & 3, r8 = lane >> 2;
+            uint4 d[4];
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
-              const int row = 8 * ps + (lane >> 2), sl = lane & 3;
-              const uint4 d = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sl ^ (row & 7)) << 4));
-              const int rr = rbase + row;
-              if (valid && rr < p.rows)
-                *reinterpret_cast<uint4*>(cb + static_cast<size_t>(rr) * p.c_row_stride + col0 + 8 * sl) = d;
+              const int row = 8 * ps + r8;
+              d[ps] = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sl ^ (row & 7)) << 4));
+            }
+            __nv_bfloat16* dst = cb + static_cast<size_t>(r8) * p.c_row_stride + col0 + 8 * sl;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              if (8 * ps + r8 < rows_here) *reinterpret_cast<uint4*>(dst) = d[ps];
+              dst += 8 * p.c_row_stride;
             }
           }
           __syncwarp();
@@ -317,30 +395,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int pending = 0;                      // staged, not yet flushed columns
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
+          const int nc = n0 + c * 32;
+          float4 bv[8];
+          if (nc < p.n) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+          }
           tmem_wait_ld();
           if (c + 1 < NC) {
             tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
           } else {
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);      // accumulator drained -> MMA may reuse it
+            release_acc(as);                       // accumulator drained -> MMA may reuse it
           }
-          const int nc = n0 + c * 32;
           if (nc < p.n) {                          // (N is a multiple of 64: chunk fully in or out)
             const uint32_t(&vc)[32] = v[c & 1];
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
             const int hslot = (pending == 32) ? 4 : 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t pk[4];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const float4 bv = (p.bias != nullptr) ? __ldg(b4 + 2 * j + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bv.x, a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bv.y;
-                float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bv.z, a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bv.w;
-                if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-                  a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
-                  a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
-                }
+                const float4 bq = bv[2 * j + h];
+                const float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bq.x, a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bq.y;
+                const float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bq.z, a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bq.w;
                 pk[2 * h] = pack_bf16x2(a0, a1);
                 pk[2 * h + 1] = pack_bf16x2(a2, a3);
               }
@@ -353,57 +430,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (c + 1 == NC && pending == 32) { flush(c * 32 - (nc < p.n ? 0 : 32), 32); pending = 0; }
         }
       } else {
-        // residual / positional addend: fetched in the MOVE layout (coalesced), one chunk ahead
+        // residual / positional addend: fetched in the MOVE layout (coalesced), one chunk ahead; the
+        // residual epilogue folds the bias into it (each thread owns 4 fixed columns per chunk)
         const float* addb;
-        if constexpr (EPI == EPI_BIAS_RESID_F32) addb = p.resid + static_cast<size_t>(b) * p.rows * p.n + n0;
-        else addb = p.pos + n0;
-        float* cb = reinterpret_cast<float*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride + n0;
+        if constexpr (EPI == EPI_BIAS_RESID_F32) addb = p.resid + (static_cast<size_t>(b) * p.rows + rbase + srow) * p.n + n0 + 4 * sslot;
+        else addb = p.pos + static_cast<size_t>(rbase + srow) * p.n + n0 + 4 * sslot;
+        float* cb = reinterpret_cast<float*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
+                    static_cast<size_t>(rbase + srow) * p.c_row_stride + n0 + 4 * sslot;
         float4 add[2][8];
         auto load_add = [&](int c, float4 (&dst)[8]) {
+          const float* src = addb + c * 32;
 #pragma unroll
           for (int ps = 0; ps < 8; ++ps) {
-            const int rr = rbase + 4 * ps + srow;
-            dst[ps] = (valid && rr < p.rows)
-                          ? *reinterpret_cast<const float4*>(addb + static_cast<size_t>(rr) * p.n + c * 32 + 4 * sslot)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[ps] = (4 * ps + srow < rows_here) ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+            src += 4 * static_cast<size_t>(p.n);
+          }
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            const float4 bq = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * sslot);
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) { dst[ps].x += bq.x; dst[ps].y += bq.y; dst[ps].z += bq.z; dst[ps].w += bq.w; }
           }
         };
         tmem_ld32(t_acc, v[0]);
         load_add(0, add[0]);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
+          float4 bv[8];
+          if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+          }
           tmem_wait_ld();
           if (c + 1 < NC) {
             tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
             load_add(c + 1, add[(c + 1) & 1]);
           } else {
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);
+            release_acc(as);
           }
           const uint32_t(&vc)[32] = v[c & 1];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 bv = (p.bias != nullptr) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float a0 = __uint_as_float(vc[4 * j]) + bv.x, a1 = __uint_as_float(vc[4 * j + 1]) + bv.y;
-            float a2 = __uint_as_float(vc[4 * j + 2]) + bv.z, a3 = __uint_as_float(vc[4 * j + 3]) + bv.w;
+            float a0 = __uint_as_float(vc[4 * j]), a1 = __uint_as_float(vc[4 * j + 1]);
+            float a2 = __uint_as_float(vc[4 * j + 2]), a3 = __uint_as_float(vc[4 * j + 3]);
             if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-              a0 = gelu_erf_fast(a0); a1 = gelu_erf_fast(a1);
-              a2 = gelu_erf_fast(a2); a3 = gelu_erf_fast(a3);
+              a0 = gelu_erf_fast(a0 + bv[j].x); a1 = gelu_erf_fast(a1 + bv[j].y);
+              a2 = gelu_erf_fast(a2 + bv[j].z); a3 = gelu_erf_fast(a3 + bv[j].w);
             }
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stg_row + ((j ^ (lane & 7)) << 4)),
                          "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
           }
           __syncwarp();
+          float* dst = cb + c * 32;
 #pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = 4 * ps + srow;
-            float4 d = *reinterpret_cast<const float4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
-            const float4 ad = add[c & 1][ps];
-            d.x += ad.x; d.y += ad.y; d.z += ad.z; d.w += ad.w;
-            const int rr = rbase + row;
-            if (valid && rr < p.rows)
-              *reinterpret_cast<float4*>(cb + static_cast<size_t>(rr) * p.c_row_stride + c * 32 + 4 * sslot) = d;
+          for (int g4 = 0; g4 < 2; ++g4) {       // 4 shared loads in flight, then their 4 stores
+            float4 d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int row = 4 * (4 * g4 + k) + srow;
+              d[k] = *reinterpret_cast<const float4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 ad = add[c & 1][4 * g4 + k];
+              d[k].x += ad.x; d[k].y += ad.y; d[k].z += ad.z; d[k].w += ad.w;
+              if (4 * (4 * g4 + k) + srow < rows_here) *reinterpret_cast<float4*>(dst) = d[k];
+              dst += 4 * p.c_row_stride;
+            }
           }
           __syncwarp();
         }
@@ -414,10 +506,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
+  if constexpr (MC > 1) cluster_sync_all();   // no CTA leaves while the pair's MMAs / arrivals may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (MC == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    else tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 

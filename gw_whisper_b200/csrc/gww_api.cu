@@ -241,7 +241,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   auto kern = gemm_tc_kernel<BN, EPI, MC>;
   if (!attr_set) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN>::kTotal));
+                                GemmSmem<BN, MC>::kTotal));
     attr_set = true;
   }
   const int tiles_m = ((p.rows + 127) / 128) * p.batch;
@@ -249,12 +249,12 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int max_groups = g_num_sms / MC;
   const int grid = (items < max_groups ? items : max_groups) * MC;
   if constexpr (MC == 1) {
-    kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, tmR, p);
+    kern<<<grid, kGemmThreads, GemmSmem<BN, MC>::kTotal, stream>>>(tmA, tmB, tmR, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = GemmSmem<BN>::kTotal;
+    cfg.dynamicSmemBytes = GemmSmem<BN, MC>::kTotal;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -308,6 +308,16 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   const uint32_t wbox[2] = {64, (uint32_t)(g.block_n / mc)};
   GWW_TRY(make_map(&tmB, false, 2, g.w_base, wdims, wstr, wbox));
   GemmParams p = g.p;
+  if (p.n > GemmSmem<256, 1>::kBiasFloats)
+    return fail(GWW_ERR_INVALID, "gemm: N=%d exceeds the %d-column bias buffer", p.n, GemmSmem<256, 1>::kBiasFloats);
+  {
+    const int tiles_per_batch = (p.rows + 127) / 128;
+    const int tiles_n = (p.n + g.block_n - 1) / g.block_n;
+    if ((long)tiles_per_batch * p.batch * tiles_n >= (1l << 24))
+      return fail(GWW_ERR_INVALID, "gemm: too many tiles for the fast tile-index division");
+    p.magic_tiles_n = gemm_div_magic(tiles_n);
+    p.magic_tiles_per_batch = gemm_div_magic(tiles_per_batch);
+  }
   const uint64_t esz = out_f32 ? 4 : 2;
   p.c = g.c_base;
   p.c_row_stride = (long)(g.c_strides[0] / esz);
