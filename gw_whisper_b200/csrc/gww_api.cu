@@ -402,7 +402,7 @@ static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaS
     if (z0 != 0) return fail(GWW_ERR_INVALID, "attention: more than 32768 det-windows per call");
     dim3 grid((T + 255) / 256, d / 64, (unsigned)nz);
     ProfScope ps(PK_ATTN, stream);
-    attention_tc_kernel<<<grid, 384, kAttnSmemBytes, stream>>>(tmQ, tmO, ap);
+    attention_tc_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tmQ, tmO, ap);
     LAUNCH_CHECK();
   }
   return GWW_OK;
