@@ -166,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, MC == 1 ? 256 : 16);   // pair: one arrival per epilogue warp of both CTAs
+      mbar_init(bar_tempty + 8 * i, 8 * MC);   // one elected arrival per epilogue warp (of both CTAs in pair mode)
     }
     fence_mbar_init();
   }
@@ -292,11 +292,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // all of this thread's tcgen05.ld of accumulator `a` have completed (tcgen05.wait::ld precedes)
     auto release_acc = [&](int a) {
       tc_fence_before();
-      if constexpr (MC == 1) {
-        mbar_arrive(bar_tempty + 8 * a);
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * a);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (MC == 1) mbar_arrive(bar_tempty + 8 * a);
+        else mbar_arrive_cluster(tempty_leader + 8 * a);
       }
     };
     for (int item = item0; item < num_items; item += item_step) {

@@ -281,8 +281,12 @@ static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, c
   return fail(GWW_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
-// 2-CTA weight multicast pays off once there are enough tile pairs to keep every SM pair busy
-static int gemm_multicast(const GemmParams& p) {
+// CTA-pair mode (tcgen05.mma.cta_group::2) needs enough tile pairs to keep every SM pair busy.  Measured
+// inside the whisper-base step (r1, ms per step, pair vs single): qkv 24.3 / 28.3, fc2 29.0 / 33.0, but
+// out_proj 17.7 / 16.3 and fc1 (GELU epilogue) 32.4 / 30.9 -- the small-N K=512 residual GEMM is HBM-bound
+// and the GELU GEMM is bound by its epilogue's issue slots, where the pair's lock-step costs more than
+// its halved operand traffic saves.
+static int gemm_pair_mode(const GemmParams& p, int epi, int ktot) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("GWW_GEMM_MC");
@@ -290,7 +294,10 @@ static int gemm_multicast(const GemmParams& p) {
   }
   if (forced == 1 || forced == 2) return forced;
   const int tiles_m = ((p.rows + 127) / 128) * p.batch;
-  return tiles_m >= g_num_sms ? 2 : 1;
+  if (tiles_m < g_num_sms) return 1;
+  if (epi == EPI_BIAS_GELU_BF16) return 1;
+  if (epi == EPI_BIAS_RESID_F32 && ktot <= 768 && p.n <= 768) return 1;
+  return 2;
 }
 
 static int run_gemm(const GemmCall& g, cudaStream_t stream) {
@@ -304,7 +311,7 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   GWW_TRY(make_map(&tmA, false, 4, g.a_base, g.a_dims, g.a_strides, abox));
   const uint64_t wdims[2] = {(uint64_t)g.ktot, (uint64_t)g.p.n};
   const uint64_t wstr[1] = {(uint64_t)g.ktot * 2};
-  const int mc = gemm_multicast(g.p);
+  const int mc = gemm_pair_mode(g.p, g.epi, g.ktot);
   const uint32_t wbox[2] = {64, (uint32_t)(g.block_n / mc)};
   GWW_TRY(make_map(&tmB, false, 2, g.w_base, wdims, wstr, wbox));
   GemmParams p = g.p;
@@ -378,14 +385,35 @@ static int pick_block_n(int n) {
 // ------------------------------------------------------------------------------------------------
 // attention / layernorm launchers
 // ------------------------------------------------------------------------------------------------
-static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaStream_t stream) {
-  if (d % 64 != 0) return fail(GWW_ERR_INVALID, "attention: d_model %% 64 != 0");
+template <int NT>
+static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmO, const AttnParams& ap, long n, int T, int d,
+                            cudaStream_t stream) {
   static bool attr_set = false;
+  auto kern = attention_tc_kernel<NT>;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kAttnSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<NT>::kSmemBytes));
     attr_set = true;
   }
+  if (n > 32768) return fail(GWW_ERR_INVALID, "attention: more than 32768 det-windows per call");   // gridDim.z limit
+  dim3 grid((T + 128 * NT - 1) / (128 * NT), d / 64, (unsigned)n);
+  ProfScope ps(PK_ATTN, stream);
+  kern<<<grid, AttnCfg<NT>::kThreads, AttnCfg<NT>::kSmemBytes, stream>>>(tmQ, tmO, ap);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
+// query tiles per CTA: 1 = two independent CTAs per SM (default), 2 = one CTA with both tiles
+static int attention_tiles_per_cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GWW_ATTN_NT");
+    v = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
+
+static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaStream_t stream) {
+  if (d % 64 != 0) return fail(GWW_ERR_INVALID, "attention: d_model %% 64 != 0");
   CUtensorMap tmQ, tmO;
   const uint64_t qd[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)n};
   const uint64_t qs[2] = {(uint64_t)6 * d, (uint64_t)T * 6 * d};
@@ -397,15 +425,8 @@ static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaS
   GWW_TRY(make_map(&tmO, false, 3, out, od, os, ob));
   AttnParams ap;
   ap.T = T; ap.d_model = d; ap.nkv = (T + 127) / 128;
-  for (long z0 = 0; z0 < n; z0 += 32768) {   // gridDim.z limit
-    const long nz = (n - z0 < 32768) ? n - z0 : 32768;
-    if (z0 != 0) return fail(GWW_ERR_INVALID, "attention: more than 32768 det-windows per call");
-    dim3 grid((T + 255) / 256, d / 64, (unsigned)nz);
-    ProfScope ps(PK_ATTN, stream);
-    attention_tc_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(tmQ, tmO, ap);
-    LAUNCH_CHECK();
-  }
-  return GWW_OK;
+  if (attention_tiles_per_cta() == 2) return launch_attention<2>(tmQ, tmO, ap, n, T, d, stream);
+  return launch_attention<1>(tmQ, tmO, ap, n, T, d, stream);
 }
 
 template <typename OutT>

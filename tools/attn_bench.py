@@ -1,0 +1,48 @@
+"""Times the fused attention kernel alone through the C ABI (gww_attention), CUDA events on the
+launching stream.  Tuning tool: A/B kernel builds with GWW_LIB=...
+    python tools/attn_bench.py [--det-windows 256] [--d 512] [--reps 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from gw_whisper_b200 import _lib  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--det-windows", type=int, default=256)
+ap.add_argument("--d", type=int, default=512)
+ap.add_argument("--T", type=int, default=1500)
+ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+a = ap.parse_args()
+lib = _lib.load()
+dev = torch.device("cuda:0")
+n, T, d = a.det_windows, a.T, a.d
+qkv = (torch.randn(n, T, 3 * d, device=dev) * 1.0).bfloat16()
+out = torch.empty(n, T, d, device=dev, dtype=torch.bfloat16)
+
+
+def run():
+    _lib.check(lib.gww_attention(qkv.data_ptr(), out.data_ptr(), n, T, d, _lib.stream_ptr()))
+
+
+for _ in range(a.warmup):
+    run()
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.reps + 1)]
+ev[0].record()
+for i in range(a.reps):
+    run()
+    ev[i + 1].record()
+torch.cuda.synchronize()
+ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(a.reps))
+med = ts[len(ts) // 2]
+flops = 4.0 * n * (d // 64) * T * T * 64
+exps = float(n) * (d // 64) * T * T
+print(json.dumps({"lib": os.path.basename(os.environ.get("GWW_LIB", "default")), "n": n, "T": T, "d": d,
+                  "ms": round(med, 4), "min_ms": round(ts[0], 4), "tflops": round(flops / med / 1e9, 1),
+                  "gexp_per_s": round(exps / med / 1e6, 1)}))
