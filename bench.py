@@ -453,7 +453,7 @@ def main():
     ap.add_argument("--model", default="base", choices=["tiny", "base", "small"])
     ap.add_argument("--batch", type=int, default=1024, help="windows per step per GPU")
     ap.add_argument("--chunk", type=int, default=256, help="det-windows per encoder pass")
-    ap.add_argument("--ref-windows", type=int, default=8, help="windows per step of the CPU reference arm")
+    ap.add_argument("--ref-windows", type=int, default=40, help="windows per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="svn", choices=["svn", "mlgwsc"],
                     help="svn = headline (configs[1]); mlgwsc = Q front end path (configs[3], 1 GPU, extra)")

@@ -53,6 +53,7 @@ constexpr int kAttnStagger = GWW_ATTN_STAGGER;
 // Ablation builds for bottleneck hunting (WRONG numerics, tools/attn_bench.py only; default 0):
 //   bit 0: odd exponentials skip the MUFU   bit 1: all exponentials skip the MUFU
 //   bit 2: no row-sum FADDs                 bit 3: no row-max pass
+//   bit 4: softmax never waits for s_full / pv_done (races)   bit 5: no TMEM loads / stores in softmax
 #ifndef GWW_ATTN_ABLATE
 #define GWW_ATTN_ABLATE 0
 #endif
@@ -312,14 +313,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
 
     auto tile = [&](const int j, auto mask_tag) {
       constexpr bool kMask = decltype(mask_tag)::value;
-      mbar_wait(b_sfull, j & 1);
+      if (!(kAttnAblate & 16)) mbar_wait(b_sfull, j & 1);
       tc_fence_after();
       uint32_t s[4][32];
-      tmem_ld32(tS + 0, s[0]);
-      tmem_ld32(tS + 32, s[1]);
-      tmem_ld32(tS + 64, s[2]);
-      tmem_ld32(tS + 96, s[3]);
-      tmem_wait_ld();
+      if (!(kAttnAblate & 32)) {
+        tmem_ld32(tS + 0, s[0]);
+        tmem_ld32(tS + 32, s[1]);
+        tmem_ld32(tS + 64, s[2]);
+        tmem_ld32(tS + 96, s[3]);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(0.01f * (i + c + lane + j));
+      }
       tc_fence_before();
       __syncwarp();                              // (32 per-thread arrivals on one barrier word serialise)
       if (lane == 0) mbar_arrive(b_sfree);       // S_t is in registers: the next Q.K^T may overwrite it
@@ -402,11 +410,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
         }
         if (c & 1) {                                 // 64 columns packed -> 32 TMEM columns of P
           if (!pv_waited) {
-            mbar_wait(b_pvdone, (j - 1) & 1);        // P_t(j-1).V finished reading P_t
+            if (!(kAttnAblate & 16)) mbar_wait(b_pvdone, (j - 1) & 1);        // P_t(j-1).V finished reading P_t
             tc_fence_after();
             pv_waited = true;
           }
-          tmem_st32(tP + (c >> 1) * 32, pk);
+          if (!(kAttnAblate & 32)) tmem_st32(tP + (c >> 1) * 32, pk);
+          else asm volatile("" ::"r"(pk[0] ^ pk[7] ^ pk[13] ^ pk[31]));
         }
       }
       l += l0 + l1;
