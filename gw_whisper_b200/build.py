@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgww_b200.so")
 SOURCES = ["gww_api.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attention_tc.cuh", "elementwise.cuh", "logmel.cuh", "qfront.cuh",
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attention_tc.cuh", "attention_persist.cuh", "elementwise.cuh", "logmel.cuh", "qfront.cuh",
            os.path.join("..", "..", "include", "gww.h")]
 
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "attention_tc.cuh"
+#include "attention_persist.cuh"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "logmel.cuh"
@@ -412,6 +413,16 @@ static int attention_tiles_per_cta() {
   return v;
 }
 
+// persistent one-CTA-per-SM kernel (default) vs one CTA per work item (GWW_ATTN_PERSIST=0)
+static bool attention_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GWW_ATTN_PERSIST");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaStream_t stream) {
   if (d % 64 != 0) return fail(GWW_ERR_INVALID, "attention: d_model %% 64 != 0");
   CUtensorMap tmQ, tmO;
@@ -423,6 +434,23 @@ static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaS
   const uint64_t os[2] = {(uint64_t)2 * d, (uint64_t)T * 2 * d};
   const uint32_t ob[3] = {64, 32, 1};
   GWW_TRY(make_map(&tmO, false, 3, out, od, os, ob));
+  if (attention_persistent()) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_TRY(cudaFuncSetAttribute(attention_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBytes));
+      attr_set = true;
+    }
+    AttnPersistParams pp;
+    pp.T = T; pp.d_model = d; pp.nkv = (T + 127) / 128; pp.n_heads = d / 64; pp.n_qpairs = (T + 255) / 256;
+    const long items = (long)pp.n_qpairs * pp.n_heads * n;
+    if (items > 0x7fffffffL) return fail(GWW_ERR_INVALID, "attention: too many work items");
+    pp.n_items = (int)items;
+    const int grid = items < g_num_sms ? (int)items : g_num_sms;
+    ProfScope ps(PK_ATTN, stream);
+    attention_persist_kernel<<<grid, 384, kApSmemBytes, stream>>>(tmQ, tmO, pp);
+    LAUNCH_CHECK();
+    return GWW_OK;
+  }
   AttnParams ap;
   ap.T = T; ap.d_model = d; ap.nkv = (T + 127) / 128;
   if (attention_tiles_per_cta() == 2) return launch_attention<2>(tmQ, tmO, ap, n, T, d, stream);
