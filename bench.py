@@ -389,14 +389,16 @@ def run_b200(args):
     att_ms, att_n = ms_k[ia], cnt_k[ia]
     att_flops = fl["attention"] * n_dw * args.steps
     att_tf = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "attention_tc_kernel (tcgen05 QK^T / PV, softmax on MUFU)",
+    roofline = {"bound": "tensor", "kernel": "attention_persist_kernel (tcgen05 QK^T / PV, softmax on MUFU)",
                 "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf,
                 "traffic": traffic_of("attention_tc_kernel"),
                 "algorithmic_bytes_per_launch": args.chunk * 1500 * (3 * d + d) * 2,
                 "peak_source": peak_src, "flops_per_launch": att_flops / max(att_n, 1),
                 "avg_launch_ms": att_ms / max(att_n, 1), "share_of_step": att_ms / max(sum(ms_k), 1e-9),
-                "note": "head_dim 64: 2 exp per 256 MAC -> MUFU.EX2 (16/clk/SM) needs 2x the tensor time of a tile; "
-                        "tensor-pipe ceiling of this kernel is ~50% of peak (profiles/r1_attention_ncu.txt)"}
+                "note": "head_dim 64: one exp per 128 MAC, so the softmax (MUFU.EX2 16/clk/SM, sharing the XU pipe with the "
+                        "bf16 packing) needs >= 2x the tensor time of a tile: the tensor-pipe ceiling of this kernel is "
+                        "~45% of peak (profiles/r1_ubench_softmax_mix.txt: 12.7 of 16 exp/clk/SM is the instruction-mix "
+                        "ceiling at two softmax warps per sub-partition; ncu: XU 68%, tensor 34% active)"}
     if "logmel" in kernels:
         lm_bytes = (2048 * 4 + 3002 * 80 * 2) * n_dw   # fused path writes bf16 time-major features
         kernels["logmel"]["gbs"] = lm_bytes / (kernels["logmel"]["ms_per_step"] * 1e-3) / 1e9
