@@ -782,6 +782,9 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
   const int d = m->cfg.d_model, f = m->cfg.ffn_dim;
   const long M = (long)nc * GWW_N_CTX;
   const int bn_d = pick_block_n(d), bn_3d = pick_block_n(3 * d), bn_f = pick_block_n(f);
+  // out_proj (K = N = d) is HBM-bound (10 d bytes per row against 2 d^2 FLOP): a 128-wide N tile leaves room
+  // for more operand stages in flight and measured 0.355 vs 0.449 ms (whisper-base, 384k rows; 5.5 TB/s)
+  const int bn_o = (d % 128 == 0) ? 128 : bn_d;
   __nv_bfloat16* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
   {  // zero pad row (t = -1) of every sample
     zero_rows_kernel<<<nc, 128, 0, stream>>>(reinterpret_cast<uint4*>(h1), (size_t)3001 * d * 2 / 16, d * 2 / 16);
@@ -843,7 +846,7 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
     GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
     GWW_TRY(run_attention(qkv, ws.h, nc, GWW_N_CTX, d, stream));
-    GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_O));
+    GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_o, stream, PK_GEMM_O));
     GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln2_g, ld.ln2_b, M, d, 0, 1, stream));
     GWW_TRY(run_linear(ws.h, ld.fc1_w, ws.g, ld.fc1_b, nullptr, M, f, d, EPI_BIAS_GELU_BF16, bn_f, stream, PK_GEMM_FC1));
     GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x, ld.fc2_b, ws.x, M, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2));

@@ -20,6 +20,7 @@ ap.add_argument("--det-windows", type=int, default=256)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--only", default="")
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--bn", type=int, default=0, help="force the N tile (128/192/256)")
 a = ap.parse_args()
 d, ffn = DIMS[a.model]
 M = a.det_windows * 1500
@@ -42,7 +43,7 @@ for name, (N, K, epi) in shapes.items():
     out_f32 = epi in (2, 3)
     Cm = torch.empty(M, N, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
     resid = torch.randn(M, N, device=dev) if epi == 2 else None
-    bn = 256 if N % 256 == 0 else (192 if N % 192 == 0 else 128)
+    bn = a.bn or (256 if N % 256 == 0 else (192 if N % 192 == 0 else 128))
 
     def run():
         _lib.check(lib.gww_gemm_bf16(A.data_ptr(), W.data_ptr(), Cm.data_ptr(), bias.data_ptr(), _lib.ptr(resid),
