@@ -44,6 +44,9 @@ constexpr int kApStages = 3;
 #endif
 constexpr int kApGroup = GWW_AP_GROUP;
 constexpr int kApLookahead = GWW_AP_LOOKAHEAD;
+#ifndef GWW_AP_PACKED_F32
+#define GWW_AP_PACKED_F32 1   // scale-subtract and row-sum on packed fp32 pairs (FFMA2 / FADD2)
+#endif
 #ifndef GWW_ATTN_POLL_NS
 #define GWW_ATTN_POLL_NS 64   // back-off of the MMA warp's polling loop when nothing is ready
 #endif
@@ -353,10 +356,18 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
               mneg_g = (g >= kApLookahead) ? fmaf(lsnap[g - kApLookahead], 0.0f, mneg) : mneg;   // == mneg
             }
           }
+#if GWW_AP_PACKED_F32
+          float x0, x1;                              // FFMA2 / FADD2: half the fp32-pipe instructions
+          ffma2_bcast(x0, x1, __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]), kLog2e, mneg_g);
+          const float p0 = fast_exp2(x0);
+          const float p1 = fast_exp2(x1);
+          fadd2_acc(l0, l1, p0, p1);
+#else
           const float p0 = fast_exp2(fmaf(__uint_as_float(s[c][i]), kLog2e, mneg_g));
           const float p1 = fast_exp2(fmaf(__uint_as_float(s[c][i + 1]), kLog2e, mneg_g));
           l0 += p0;
           l1 += p1;
+#endif
           pk[(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
         }
         if (c & 1) {                                 // 64 keys packed -> 32 TMEM columns of P: half c >> 1
