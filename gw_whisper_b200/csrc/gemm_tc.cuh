@@ -53,7 +53,25 @@ struct GemmParams {
   // x < 2^24, d < 2^16) -- the per-tile index math must not cost integer divisions in the single-thread loops
   unsigned long long magic_tiles_n;
   unsigned long long magic_tiles_per_batch;
+  // ---- LayerNorm folding (see "LayerNorm folding" below).  Producer side (f32-output epilogues):
+  __nv_bfloat16* xb;     // bf16 copy of the output rows [batch*rows, n] (the next GEMM's A operand) or nullptr
+  float* stats_out;      // per-row partial (sum, sum of squares): [batch*rows][stat_slots][2], slot = 2*n_tile + half
+  // consumer side (bf16-output epilogues): out = rs * acc - rs * mu * c1[n] + c2[n], c2 passed as `bias`
+  const float* stats_in; // the producer's partials for the rows of A, or nullptr (plain bias epilogue)
+  const float* ln_c1;    // [n] column sums of the gamma-scaled (bf16-rounded) weights
+  int stat_slots;        // partial slots per row written (producer) / to be summed (consumer)
+  float ln_inv_k;        // 1 / d_model
+  float ln_eps;
 };
+
+// LayerNorm folding.  h = LN(x) feeds only a Linear: LN(x) W^T + b = rs * (x (g.W)^T) - rs * mu * c1 + c2 with
+// c1[n] = sum_k g_k W_nk and c2[n] = sum_k beta_k W_nk + b_n.  So the GEMM that PRODUCES the residual stream x
+// also writes its bf16 copy and per-row partial sums of x and x^2 (in fixed slots: deterministic, no atomics,
+// no memset), and the consuming GEMM runs on the raw bf16 x with gamma-scaled weights and applies the two
+// per-row scalars in its epilogue.  The stand-alone LayerNorm kernel (6 d bytes of HBM traffic per row, 7 % of
+// the whisper-base step) disappears.  Rounding: bf16(x) against bf16(LN(x)) -- measured equal to within 5 %
+// on every layer of the random-init and spread-scaled encoders (|mu| / sigma <= 1.2); models whose residual
+// stream has |mu| >> sigma should keep the LayerNorm kernel (GWW_LN_FOLD=0).
 
 __host__ __device__ __forceinline__ unsigned long long gemm_div_magic(int d) {
   return ((1ull << 40) / static_cast<unsigned long long>(d)) + 1ull;
@@ -77,9 +95,8 @@ __device__ __forceinline__ float gelu_erf_fast(float v) {
 
 // The same GELU on a PAIR of values with packed fp32 math (FMUL2 / FFMA2): 7 packed + 2 FMNMX + 2 MUFU
 // instructions per pair instead of 18; the GELU epilogues are bound by their issue slots.
-//   in : acc pair (a0, a1) and bias pair (b0, b1);  out: gelu(a0 + b0), gelu(a1 + b1)
-__device__ __forceinline__ void gelu_erf_fast2(float a0, float a1, float b0, float b1, float& g0, float& g1) {
-  const uint64_t v = f2_add(f2_pack(a0, a1), f2_pack(b0, b1));
+//   in : packed pre-activation pair v;  out: gelu(v.lo), gelu(v.hi)
+__device__ __forceinline__ void gelu_erf_fast2(const uint64_t v, float& g0, float& g1) {
   float q0, q1;
   f2_unpack(f2_mul(v, v), q0, q1);
   const uint64_t v2 = f2_pack(fminf(q0, 36.0f), fminf(q1, 36.0f));
@@ -104,7 +121,7 @@ struct GemmSmem {
   static constexpr int kBarBytes = 192;  // (2*stages+4) mbarriers + tmem ptr, stages <= 6
   static constexpr int kStagingBytes = 8 * 4096;   // one 32-row x 128-byte transpose buffer per epilogue warp
   static constexpr int kBiasFloats = 3072;         // the whole bias vector lives in smem (N <= 3072)
-  static constexpr int kBiasBytes = kBiasFloats * 4;
+  static constexpr int kBiasBytes = 2 * kBiasFloats * 4;   // bias (or c2) and the LayerNorm-fold column sums c1
   static constexpr int kLimit = 232448 - 1024;     // 227 KB opt-in minus the 1 KB reserved for __align__(1024)
   static constexpr int kFit = (kLimit - kStagingBytes - kBiasBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kFit > 6 ? 6 : kFit;
@@ -143,6 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* stage_base = smem;
   uint8_t* staging_base = smem + kStages * S::kStageBytes;
   float* bias_s = reinterpret_cast<float*>(staging_base + S::kStagingBytes);
+  float* c1_s = bias_s + S::kBiasFloats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging_base + S::kStagingBytes + S::kBiasBytes);
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   const uint32_t bar_full = smem_u32(bars);
@@ -176,7 +194,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   // the bias vector is read by every epilogue thread for every tile: keep it in shared memory (the r1
   // profile showed the per-chunk global bias loads missing L1 and stalling each chunk ~500 clocks)
-  for (int i = threadIdx.x; i < p.n; i += kGemmThreads) bias_s[i] = (p.bias != nullptr) ? p.bias[i] : 0.0f;
+  for (int i = threadIdx.x; i < p.n; i += kGemmThreads) {
+    bias_s[i] = (p.bias != nullptr) ? p.bias[i] : 0.0f;
+    c1_s[i] = (p.stats_in != nullptr) ? p.ln_c1[i] : 0.0f;
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
@@ -325,7 +346,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rbase = r0 + q * 32;          // first row of this warp inside the batch entry
       const int rows_here = valid ? (p.rows - rbase) : 0;   // rows [0, rows_here) of this warp's 32 exist
       const float* bias_w = bias_s + n0;      // this warp's bias slice (may run past N for a ragged last tile)
+      const float* c1_w = c1_s + n0;
 
+      // LayerNorm fold: this thread's row scalars (rs, -rs*mu); (1, 0) makes the epilogue a plain bias add
+      uint64_t rs2 = f2_pack(1.0f, 1.0f), nmr2 = f2_pack(0.0f, 0.0f);
+      if constexpr (!kOutF32) {
+        if (p.stats_in != nullptr) {
+          float s1 = 0.f, s2 = 0.f;
+          if (lane < rows_here) {
+            const float2* st = reinterpret_cast<const float2*>(p.stats_in) +
+                               (static_cast<size_t>(b) * p.rows + rbase + lane) * p.stat_slots;
+            for (int i = 0; i < p.stat_slots; ++i) { const float2 v2 = __ldg(st + i); s1 += v2.x; s2 += v2.y; }
+          }
+          const float mu = s1 * p.ln_inv_k;
+          const float var = fmaxf(s2 * p.ln_inv_k - mu * mu, 0.0f);
+          const float rs = rsqrtf(var + p.ln_eps);
+          rs2 = f2_pack(rs, rs);
+          nmr2 = f2_pack(-rs * mu, -rs * mu);
+        }
+      }
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * HW;
@@ -339,10 +378,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int nc = n0 + c * 32;
-          float4 bv[8];
+          float4 bv[8], cv[8];
           if (nc < p.n) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+            for (int j = 0; j < 8; ++j) {
+              bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+              cv[j] = *reinterpret_cast<const float4*>(c1_w + c * 32 + 4 * j);
+            }
           }
           tmem_wait_ld();
           if (c + 1 < NC) {
@@ -356,8 +398,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float a0, a1, a2, a3;
-              gelu_erf_fast2(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1]), bv[j].x, bv[j].y, a0, a1);
-              gelu_erf_fast2(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3]), bv[j].z, bv[j].w, a2, a3);
+              gelu_erf_fast2(f2_fma(f2_pack(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1])), rs2,
+                                    f2_fma(f2_pack(cv[j].x, cv[j].y), nmr2, f2_pack(bv[j].x, bv[j].y))), a0, a1);
+              gelu_erf_fast2(f2_fma(f2_pack(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3])), rs2,
+                                    f2_fma(f2_pack(cv[j].z, cv[j].w), nmr2, f2_pack(bv[j].z, bv[j].w))), a2, a3);
               pk[2 * j] = pack_bf16x2(a0, a1);
               pk[2 * j + 1] = pack_bf16x2(a2, a3);
             }
@@ -412,10 +456,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int nc = n0 + c * 32;
-          float4 bv[8];
+          float4 bv[8], cv[8];
           if (nc < p.n) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+            for (int j = 0; j < 8; ++j) {
+              bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+              cv[j] = *reinterpret_cast<const float4*>(c1_w + c * 32 + 4 * j);
+            }
           }
           tmem_wait_ld();
           if (c + 1 < NC) {
@@ -431,9 +478,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t pk[4];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const float4 bq = bv[2 * j + h];
-                const float a0 = __uint_as_float(vc[8 * j + 4 * h]) + bq.x, a1 = __uint_as_float(vc[8 * j + 4 * h + 1]) + bq.y;
-                const float a2 = __uint_as_float(vc[8 * j + 4 * h + 2]) + bq.z, a3 = __uint_as_float(vc[8 * j + 4 * h + 3]) + bq.w;
+                const float4 bq = bv[2 * j + h], cq = cv[2 * j + h];
+                float a0, a1, a2, a3;     // rs * acc + (-rs*mu * c1 + c2); (rs, -rs*mu) = (1, 0) without the fold
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(vc[8 * j + 4 * h]), __uint_as_float(vc[8 * j + 4 * h + 1])), rs2,
+                                 f2_fma(f2_pack(cq.x, cq.y), nmr2, f2_pack(bq.x, bq.y))), a0, a1);
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(vc[8 * j + 4 * h + 2]), __uint_as_float(vc[8 * j + 4 * h + 3])), rs2,
+                                 f2_fma(f2_pack(cq.z, cq.w), nmr2, f2_pack(bq.z, bq.w))), a2, a3);
                 pk[2 * h] = pack_bf16x2(a0, a1);
                 pk[2 * h + 1] = pack_bf16x2(a2, a3);
               }
@@ -467,6 +517,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int ps = 0; ps < 8; ++ps) { dst[ps].x += bq.x; dst[ps].y += bq.y; dst[ps].z += bq.z; dst[ps].w += bq.w; }
           }
         };
+        __nv_bfloat16* xbp = (p.xb != nullptr)
+                                 ? p.xb + (static_cast<size_t>(b) * p.rows + rbase + srow) * p.n + n0 + 4 * sslot
+                                 : nullptr;
+        float rsum[8], rsq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rsum[i] = 0.f; rsq[i] = 0.f; }
         tmem_ld32(t_acc, v[0]);
         load_add(0, add[0]);
 #pragma unroll
@@ -489,8 +545,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float a0 = __uint_as_float(vc[4 * j]), a1 = __uint_as_float(vc[4 * j + 1]);
             float a2 = __uint_as_float(vc[4 * j + 2]), a3 = __uint_as_float(vc[4 * j + 3]);
             if constexpr (EPI == EPI_BIAS_GELU_POS_F32) {
-              gelu_erf_fast2(a0, a1, bv[j].x, bv[j].y, a0, a1);
-              gelu_erf_fast2(a2, a3, bv[j].z, bv[j].w, a2, a3);
+              gelu_erf_fast2(f2_add(f2_pack(a0, a1), f2_pack(bv[j].x, bv[j].y)), a0, a1);
+              gelu_erf_fast2(f2_add(f2_pack(a2, a3), f2_pack(bv[j].z, bv[j].w)), a2, a3);
             }
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stg_row + ((j ^ (lane & 7)) << 4)),
                          "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
@@ -509,11 +565,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < 4; ++k) {
               const float4 ad = add[c & 1][4 * g4 + k];
               d[k].x += ad.x; d[k].y += ad.y; d[k].z += ad.z; d[k].w += ad.w;
-              if (4 * (4 * g4 + k) + srow < rows_here) *reinterpret_cast<float4*>(dst) = d[k];
+              const bool rok = 4 * (4 * g4 + k) + srow < rows_here;
+              if (rok) *reinterpret_cast<float4*>(dst) = d[k];
               dst += 4 * p.c_row_stride;
+              if (xbp != nullptr) {
+                if (rok) *reinterpret_cast<uint2*>(xbp + static_cast<size_t>(4 * (4 * g4 + k)) * p.n + c * 32) =
+                    make_uint2(pack_bf16x2(d[k].x, d[k].y), pack_bf16x2(d[k].z, d[k].w));
+                rsum[4 * g4 + k] += (d[k].x + d[k].y) + (d[k].z + d[k].w);
+                rsq[4 * g4 + k] += fmaf(d[k].x, d[k].x, d[k].y * d[k].y) + fmaf(d[k].z, d[k].z, d[k].w * d[k].w);
+              }
             }
           }
           __syncwarp();
+        }
+        if (p.stats_out != nullptr) {
+          // this warp's partial over its HW columns: combine the 8 lanes that share a row, store to the slot
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              rsum[i] += __shfl_xor_sync(0xffffffffu, rsum[i], o);
+              rsq[i] += __shfl_xor_sync(0xffffffffu, rsq[i], o);
+            }
+          }
+          if (sslot == 0) {
+            const int slot = 2 * n_idx + half;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = 4 * i + srow;
+              if (row < rows_here)
+                reinterpret_cast<float2*>(p.stats_out)[(static_cast<size_t>(b) * p.rows + rbase + row) * p.stat_slots + slot] =
+                    make_float2(rsum[i], rsq[i]);
+            }
+          }
         }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }

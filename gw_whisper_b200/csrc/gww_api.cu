@@ -218,6 +218,7 @@ static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* bas
 // ------------------------------------------------------------------------------------------------
 // GEMM dispatch
 // ------------------------------------------------------------------------------------------------
+constexpr int kStatSlotsMax = 16;
 struct GemmCall {
   // A operand: 4-D view {C, P, R, Bt} of a bf16 activation
   const void* a_base;
@@ -355,9 +356,29 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
 }
 
 // plain Linear: C[M,N] = epi(A[M,K] W[N,K]^T)
+// LayerNorm-fold plumbing of one Linear: producer side (writes xb + stats) or consumer side (reads them)
+struct LnFold {
+  __nv_bfloat16* xb = nullptr;
+  float* stats_out = nullptr;
+  const float* stats_in = nullptr;
+  const float* c1 = nullptr;
+  int in_slots = 0;     // slots the producer of stats_in wrote
+  int d_model = 0;
+};
+static int stat_slots_of(int n, int block_n) { return 2 * ((n + block_n - 1) / block_n); }
+static void apply_fold(GemmParams& p, const LnFold& lf, int block_n) {
+  p.xb = lf.xb;
+  p.stats_out = lf.stats_out;
+  p.stats_in = lf.stats_in;
+  p.ln_c1 = lf.c1;
+  p.stat_slots = lf.stats_in ? lf.in_slots : stat_slots_of(p.n, block_n);
+  p.ln_inv_k = lf.d_model > 0 ? 1.0f / (float)lf.d_model : 0.f;
+  p.ln_eps = 1e-5f;
+}
+
 static int run_linear(const void* A, const void* W, void* C, const float* bias, const float* resid,
                       long M, int N, int K, int epi, int block_n, cudaStream_t stream,
-                      int kind = PK_OTHER) {
+                      int kind = PK_OTHER, const LnFold& lf = LnFold()) {
   GemmCall g{};
   g.kind = kind;
   g.a_base = A;
@@ -374,6 +395,9 @@ static int run_linear(const void* A, const void* W, void* C, const float* bias, 
   g.p.bias = bias; g.p.resid = resid; g.p.pos = nullptr;
   g.epi = epi;
   g.block_n = block_n;
+  apply_fold(g.p, lf, block_n);
+  if (g.p.stats_out && g.p.stat_slots > kStatSlotsMax)
+    return fail(GWW_ERR_INVALID, "gemm: %d statistic slots exceed the workspace layout", g.p.stat_slots);
   return run_gemm(g, stream);
 }
 
@@ -577,6 +601,10 @@ struct LayerDev {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
   float *qkv_b, *o_b, *fc1_b, *fc2_b;
+  // LayerNorm folded into the consuming Linear (gemm_tc.cuh "LayerNorm folding"): W (.) gamma in bf16,
+  // c1[n] = sum_k of those bf16 weights, c2[n] = sum_k beta_k W_nk + b_n
+  __nv_bfloat16 *qkv_wf, *fc1_wf;
+  float *qkv_c1, *qkv_c2, *fc1_c1, *fc1_c2;
 };
 struct gww_model {
   gww_encoder_config_t cfg;
@@ -625,6 +653,25 @@ static void dora_merge(const float* W0, int dout, int din, const gww_dora_t& a, 
     for (int i = 0; i < din; ++i) nrm += (double)row[i] * row[i];
     const float sc = (float)((double)a.magnitude[o] / std::sqrt(nrm));
     for (int i = 0; i < din; ++i) row[i] *= sc;
+  }
+}
+
+// folds LayerNorm(gamma, beta) into the Linear (W [N,K], b [N]) that consumes it
+static void ln_fold(const std::vector<float>& W, const float* b, const float* gamma, const float* beta, int N, int K,
+                    std::vector<float>& Wf, std::vector<float>& c1, std::vector<float>& c2) {
+  Wf.resize((size_t)N * K);
+  c1.assign(N, 0.f);
+  c2.assign(N, 0.f);
+  for (int n = 0; n < N; ++n) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const float wg = W[(size_t)n * K + k] * gamma[k];
+      Wf[(size_t)n * K + k] = wg;
+      s1 += (double)__bfloat162float(__float2bfloat16(wg));   // the sum of what the tensor core will multiply by
+      s2 += (double)beta[k] * (double)W[(size_t)n * K + k];
+    }
+    c1[n] = (float)s1;
+    c2[n] = (float)(s2 + (b ? (double)b[n] : 0.0));
   }
 }
 
@@ -683,6 +730,18 @@ extern "C" int gww_model_create(const gww_encoder_config_t* cfg, const gww_encod
     }
     guard(dev_bf16(m, qkv, &ld.qkv_w));
     guard(dev_f32(m, qkvb.data(), 3 * d, &ld.qkv_b));
+    {
+      std::vector<float> wf, c1, c2;
+      ln_fold(qkv, qkvb.data(), lw.ln1_g, lw.ln1_b, 3 * d, d, wf, c1, c2);
+      guard(dev_bf16(m, wf, &ld.qkv_wf));
+      guard(dev_f32(m, c1.data(), 3 * d, &ld.qkv_c1));
+      guard(dev_f32(m, c2.data(), 3 * d, &ld.qkv_c2));
+      const std::vector<float> w1(lw.fc1_w, lw.fc1_w + (size_t)f * d);
+      ln_fold(w1, lw.fc1_b, lw.ln2_g, lw.ln2_b, f, d, wf, c1, c2);
+      guard(dev_bf16(m, wf, &ld.fc1_wf));
+      guard(dev_f32(m, c1.data(), f, &ld.fc1_c1));
+      guard(dev_f32(m, c2.data(), f, &ld.fc1_c2));
+    }
     guard(dev_bf16(m, o, &ld.o_w));
     guard(dev_f32(m, lw.o_b, d, &ld.o_b));
     guard(dev_bf16(m, std::vector<float>(lw.fc1_w, lw.fc1_w + (size_t)f * d), &ld.fc1_w));
@@ -744,8 +803,11 @@ struct Workspace {
   float* head_scratch;      // [2, chunk, kHeadMaxWidth]
   float* gather;            // [chunk, 2048] contiguous strain windows
   float* x_last;            // [chunk, d] residual rows of the last token (pruned final layer)
+  __nv_bfloat16* xb;        // [chunk*1500, d]  bf16 copy of the residual stream (LayerNorm fold: A operand of qkv / fc1)
+  float* stats;             // [chunk*1500, kStatSlots, 2] per-row partial (sum, sum of squares) of x
   size_t total;
 };
+constexpr int kStatSlots = 16;   // 2 * ceil(d / block_n) <= 16 for d <= 1024 with block_n >= 128
 static size_t align_up(size_t v) { return (v + 1023) & ~(size_t)1023; }
 static Workspace carve(const gww_model* m, int chunk, uint8_t* base) {
   const size_t d = m->cfg.d_model, f = m->cfg.ffn_dim, M = (size_t)chunk * GWW_N_CTX;
@@ -766,6 +828,8 @@ static Workspace carve(const gww_model* m, int chunk, uint8_t* base) {
   w.head_scratch = (float*)take((size_t)2 * chunk * kHeadMaxWidth * 4);
   w.gather = (float*)take((size_t)chunk * 2048 * 4);
   w.x_last = (float*)take((size_t)chunk * d * 4);
+  w.xb = (__nv_bfloat16*)take(M * d * 2);
+  w.stats = (float*)take(M * kStatSlots * 2 * 4);
   w.total = off;
   return w;
 }
@@ -777,6 +841,16 @@ extern "C" size_t gww_workspace_bytes(const gww_model_t* m, int chunk) {
 // ------------------------------------------------------------------------------------------------
 // encoder on one chunk whose time-major bf16 features are already in ws.feats_tm
 // ------------------------------------------------------------------------------------------------
+// LayerNorm folded into the neighbouring GEMMs (default) or the stand-alone LayerNorm kernel (GWW_LN_FOLD=0)
+static bool ln_fold_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GWW_LN_FOLD");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float* last_hidden,
                          float* pooled, int use_last_token, cudaStream_t stream) {
   const int d = m->cfg.d_model, f = m->cfg.ffn_dim;
@@ -785,6 +859,12 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
   // out_proj (K = N = d) is HBM-bound (10 d bytes per row against 2 d^2 FLOP): a 128-wide N tile leaves room
   // for more operand stages in flight and measured 0.355 vs 0.449 ms (whisper-base, 384k rows; 5.5 TB/s)
   const int bn_o = (d % 128 == 0) ? 128 : bn_d;
+  const bool fold = ln_fold_enabled();
+  // producer side of a residual GEMM / consumer side of the Linear after a LayerNorm
+  auto produce = [&]() { LnFold lf; if (fold) { lf.xb = ws.xb; lf.stats_out = ws.stats; lf.d_model = d; } return lf; };
+  auto consume = [&](const float* c1, int slots) {
+    LnFold lf; lf.stats_in = ws.stats; lf.c1 = c1; lf.in_slots = slots; lf.d_model = d; return lf;
+  };
   __nv_bfloat16* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
   {  // zero pad row (t = -1) of every sample
     zero_rows_kernel<<<nc, 128, 0, stream>>>(reinterpret_cast<uint4*>(h1), (size_t)3001 * d * 2 / 16, d * 2 / 16);
@@ -814,8 +894,13 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     g.p.rows = GWW_N_CTX; g.p.batch = nc; g.p.n = d; g.p.kb_per_tap = d / 64; g.p.taps = 3; g.p.p_mod = 2;
     g.p.bias = m->conv2_b; g.p.resid = nullptr; g.p.pos = m->pos_emb;
     g.epi = EPI_BIAS_GELU_POS_F32; g.block_n = bn_d; g.kind = PK_GEMM_CONV2;
+    if (fold) {   // the first layer's LN1 statistics and bf16 copy come out of the conv stem
+      LnFold lf; lf.xb = ws.xb; lf.stats_out = ws.stats; lf.d_model = d;
+      apply_fold(g.p, lf, bn_d);
+    }
     GWW_TRY(run_gemm(g, stream));
   }
+  int slots_in = stat_slots_of(d, bn_d);   // slots written by the GEMM that last produced x
   __nv_bfloat16* qkv = ws.g;
   // when only last_hidden_state[:, -1, :] is consumed, the final layer needs all tokens'
   // K and V but only the last token's query row, out-projection, MLP and final LayerNorm.
@@ -826,8 +911,13 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
       const int T = GWW_N_CTX;
       __nv_bfloat16* hl = ws.h;                          // [nc, d] attention output of the last token
       __nv_bfloat16* hl2 = ws.h + (size_t)nc * d;        // [nc, d] LN2 output
-      GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
-      GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
+      if (fold) {
+        GWW_TRY(run_linear(ws.xb, ld.qkv_wf, qkv, ld.qkv_c2, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV,
+                           consume(ld.qkv_c1, slots_in)));
+      } else {
+        GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
+        GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
+      }
       {
         ProfScope ps(PK_ATTN_LAST, stream);
         const size_t smem = (size_t)(((T + 3) & ~3) + 8 * 64 + 16) * sizeof(float);
@@ -842,6 +932,18 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
       GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x_last, ld.fc2_b, ws.x_last, nc, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2));
       GWW_TRY(run_ln_t<float>(ws.x_last, pooled, m->lnp_g, m->lnp_b, nc, d, 0, 1, stream));
       return GWW_OK;
+    }
+    if (fold) {
+      // no LayerNorm kernels: x's bf16 copy and row statistics come out of the GEMM that produced x
+      GWW_TRY(run_linear(ws.xb, ld.qkv_wf, qkv, ld.qkv_c2, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV,
+                         consume(ld.qkv_c1, slots_in)));
+      GWW_TRY(run_attention(qkv, ws.h, nc, GWW_N_CTX, d, stream));
+      GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_o, stream, PK_GEMM_O, produce()));
+      GWW_TRY(run_linear(ws.xb, ld.fc1_wf, ws.g, ld.fc1_c2, nullptr, M, f, d, EPI_BIAS_GELU_BF16, bn_f, stream, PK_GEMM_FC1,
+                         consume(ld.fc1_c1, stat_slots_of(d, bn_o))));
+      GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x, ld.fc2_b, ws.x, M, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2, produce()));
+      slots_in = stat_slots_of(d, bn_d);
+      continue;
     }
     GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
     GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
