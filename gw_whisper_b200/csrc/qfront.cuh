@@ -480,10 +480,13 @@ qadapter_conv2_kernel(const float* __restrict__ act1, float* __restrict__ act2, 
   const int cg = threadIdx.x >> 6;              // channel group (8 channels), warp-uniform
   const int quad = threadIdx.x & 63;
   const int qy = quad >> 3, qx = quad & 7;
-  float acc[4][8];
+  // accumulators as packed fp32 PAIRS of adjacent output channels: one FFMA2 (fma.rn.f32x2, per-lane IEEE fma,
+  // bit-identical to two fmaf) per two multiply-adds -- the loop is bound by fp32 issue slots (r1: scalar FFMA tops
+  // out at 107 of the SM's 128 FMA/clk, FFMA2 reaches 126; tools/ubench/ffma2.cu)
+  uint64_t acc[4][4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float bv = bsm[cg * 8 + c];
+  for (int c = 0; c < 4; ++c) {
+    const uint64_t bv = f2_pack(bsm[cg * 8 + 2 * c], bsm[cg * 8 + 2 * c + 1]);
 #pragma unroll
     for (int px = 0; px < 4; ++px) acc[px][c] = bv;
   }
@@ -503,22 +506,28 @@ qadapter_conv2_kernel(const float* __restrict__ act1, float* __restrict__ act2, 
       for (int kx = 0; kx < 3; ++kx) {
         const float4* wp = reinterpret_cast<const float4*>(wsm + ((ky * 3 + kx) * 16 + ci) * 32 + cg * 8);
         const float4 wa = wp[0], wb = wp[1];
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const uint64_t wv[4] = {f2_pack(wa.x, wa.y), f2_pack(wa.z, wa.w), f2_pack(wb.x, wb.y), f2_pack(wb.z, wb.w)};
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 2; ++dx) {
             const float iv = p[dy + ky][dx + kx];
+            const uint64_t iv2 = f2_pack(iv, iv);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[dy * 2 + dx][c] = fmaf(iv, wv[c], acc[dy * 2 + dx][c]);
+            for (int c = 0; c < 4; ++c) acc[dy * 2 + dx][c] = f2_fma(iv2, wv[c], acc[dy * 2 + dx][c]);
           }
       }
   }
   const int PH = H >> 1, PW = W >> 1;
   float o[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    o[c] = fmaxf(fmaxf(fmaxf(acc[0][c], acc[1][c]), fmaxf(acc[2][c], acc[3][c])), 0.f);
+  for (int c = 0; c < 4; ++c) {
+    float a0[4], a1[4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) f2_unpack(acc[px][c], a0[px], a1[px]);
+    o[2 * c] = fmaxf(fmaxf(fmaxf(a0[0], a0[1]), fmaxf(a0[2], a0[3])), 0.f);
+    o[2 * c + 1] = fmaxf(fmaxf(fmaxf(a1[0], a1[1]), fmaxf(a1[2], a1[3])), 0.f);
+  }
   float4* dst = reinterpret_cast<float4*>(
       act2 + ((n * PH + ((y0 >> 1) + qy)) * static_cast<long>(PW) + ((x0 >> 1) + qx)) * 32 + cg * 8);
   dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -545,11 +554,11 @@ qadapter_conv3_kernel(const float* __restrict__ act2, float* __restrict__ map, i
   const int cg = threadIdx.x >> 6;              // 16 channels per group
   const int quad = threadIdx.x & 63;
   const int qy = quad >> 3, qx = quad & 7;
-  float acc[4][16];
+  uint64_t acc[4][8];                            // packed pairs of adjacent output channels (see conv2)
   __syncthreads();
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const float bv = bsm[cg * 16 + c];
+  for (int c = 0; c < 8; ++c) {
+    const uint64_t bv = f2_pack(bsm[cg * 16 + 2 * c], bsm[cg * 16 + 2 * c + 1]);
 #pragma unroll
     for (int px = 0; px < 4; ++px) acc[px][c] = bv;
   }
@@ -590,14 +599,16 @@ qadapter_conv3_kernel(const float* __restrict__ act2, float* __restrict__ map, i
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const float4 wv = wp[c4];
+            const uint64_t w01 = f2_pack(wv.x, wv.y), w23 = f2_pack(wv.z, wv.w);
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx) {
                 const float iv = p[dy + ky][dx + kx];
-                float* a4 = &acc[dy * 2 + dx][4 * c4];
-                a4[0] = fmaf(iv, wv.x, a4[0]); a4[1] = fmaf(iv, wv.y, a4[1]);
-                a4[2] = fmaf(iv, wv.z, a4[2]); a4[3] = fmaf(iv, wv.w, a4[3]);
+                const uint64_t iv2 = f2_pack(iv, iv);
+                uint64_t* a2 = &acc[dy * 2 + dx][2 * c4];
+                a2[0] = f2_fma(iv2, w01, a2[0]);
+                a2[1] = f2_fma(iv2, w23, a2[1]);
               }
           }
         }
@@ -608,7 +619,12 @@ qadapter_conv3_kernel(const float* __restrict__ act2, float* __restrict__ map, i
   for (int px = 0; px < 4; ++px) {
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) s = fmaf(fmaxf(acc[px][c], 0.f), w4s[cg * 16 + c], s);
+    for (int c = 0; c < 8; ++c) {
+      float a0, a1;
+      f2_unpack(acc[px][c], a0, a1);
+      s = fmaf(fmaxf(a0, 0.f), w4s[cg * 16 + 2 * c], s);
+      s = fmaf(fmaxf(a1, 0.f), w4s[cg * 16 + 2 * c + 1], s);
+    }
     red[cg * 256 + quad * 4 + px] = s;
   }
   __syncthreads();
