@@ -111,6 +111,20 @@ __device__ __forceinline__ void gelu_erf_fast2(const uint64_t v, float& g0, floa
 }
 
 constexpr int kGemmThreads = 384;   // 12 warps: TMA, MMA, TMEM alloc, spare, 8 x epilogue
+// The GELU -> bf16 epilogue (fc1, conv1) runs ~14 instructions per output pair.  GWW_GELU_EPI_WARPS=16 gives it
+// 16 epilogue warps (12 for BN = 192; a quarter / third of the tile's columns each, single-buffered TMEM loads,
+// <= 102 registers) instead of 8: measured equal in isolation (0.769 vs 0.772 ms) and slower inside the step
+// (33.5 vs 30.9 ms), so 8 stays the default -- the kernel is not short of warps but of power budget.
+#ifndef GWW_GELU_EPI_WARPS
+#define GWW_GELU_EPI_WARPS 8
+#endif
+template <int EPI, int BN>
+__host__ __device__ constexpr int gemm_epi_warps() {
+  // column parts of whole 32-column chunks: 256 / 4, 192 / 3, 128 / 4
+  return (EPI == EPI_BIAS_GELU_BF16 && GWW_GELU_EPI_WARPS == 16) ? (BN == 192 ? 12 : 16) : 8;
+}
+template <int EPI, int BN>
+__host__ __device__ constexpr int gemm_threads() { return 128 + 32 * gemm_epi_warps<EPI, BN>(); }
 
 template <int BN, int MC = 1>
 struct GemmSmem {
@@ -141,7 +155,7 @@ struct GemmSmem {
 // pair needs 32 KB per SM for the same math.  (A TMA-multicast variant was measured first: no gain,
 // since multicast saves L2 reads but not per-SM ingest.)
 template <int BN, int EPI, int MC>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI, BN>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using S = GemmSmem<BN, MC>;
@@ -194,7 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   // the bias vector is read by every epilogue thread for every tile: keep it in shared memory (the r1
   // profile showed the per-chunk global bias loads missing L1 and stalling each chunk ~500 clocks)
-  for (int i = threadIdx.x; i < p.n; i += kGemmThreads) {
+  constexpr int kEpiWarps = gemm_epi_warps<EPI, BN>();
+  for (int i = threadIdx.x; i < p.n; i += gemm_threads<EPI, BN>()) {
     bias_s[i] = (p.bias != nullptr) ? p.bias[i] : 0.0f;
     c1_s[i] = (p.stats_in != nullptr) ? p.ln_c1[i] : 0.0f;
   }
@@ -205,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 8 * MC);   // one elected arrival per epilogue warp (of both CTAs in pair mode)
+      mbar_init(bar_tempty + 8 * i, gemm_epi_warps<EPI, BN>() * MC);   // one elected arrival per epilogue warp (of both CTAs in pair mode)
     }
     fence_mbar_init();
   }
@@ -319,10 +334,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // whole 128-byte row segments per quarter-warp (4 lines per instruction instead of 32).
     const int e = warp - 4;
     const int q = e & 3;
-    const int half = e >> 2;
-    constexpr int HW = BN / 2;          // accumulator columns handled by one warp
+    const int half = e >> 2;            // column part handled by this warp (0..kEpiWarps/4-1)
+    constexpr int HW = BN / (kEpiWarps / 4);   // accumulator columns handled by one warp
     constexpr int NC = HW / 32;         // 32-column chunks per warp
-    uint8_t* stg = staging_base + e * 4096;
+    static_assert(HW % 32 == 0, "column part must be whole 32-column chunks");
+    uint8_t* stg = staging_base + (e & 7) * 4096;   // (the 16-warp GELU epilogue does not stage)
     const uint32_t stg_row = smem_u32(stg) + lane * 128;          // this thread's row while staging
     const int srow = lane >> 3, sslot = lane & 7;                 // (row-in-pass, 16-byte slot) while moving
     int as = 0;
@@ -374,44 +390,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool row_ok = lane < rows_here;
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
                               static_cast<size_t>(row_ok ? rbase + lane : 0) * p.c_row_stride + n0;
+        constexpr bool kDouble = (kEpiWarps == 8);   // 8 warps: next chunk's TMEM load in flight; 16: other warps hide it
         tmem_ld32(t_acc, v[0]);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int nc = n0 + c * 32;
-          float4 bv[8], cv[8];
-          if (nc < p.n) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              bv[j] = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
-              cv[j] = *reinterpret_cast<const float4*>(c1_w + c * 32 + 4 * j);
-            }
-          }
           tmem_wait_ld();
-          if (c + 1 < NC) {
-            tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
-          } else {
-            release_acc(as);
+          if (kDouble) {
+            if (c + 1 < NC) tmem_ld32(t_acc + (c + 1) * 32, v[(c + 1) & 1]);
+            else release_acc(as);
           }
+          const uint32_t(&vc)[32] = v[kDouble ? (c & 1) : 0];
+          uint32_t pk[16];
           if (nc < p.n) {
-            const uint32_t(&vc)[32] = v[c & 1];
-            uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+              const float4 bq = *reinterpret_cast<const float4*>(bias_w + c * 32 + 4 * j);
+              const float4 cq = *reinterpret_cast<const float4*>(c1_w + c * 32 + 4 * j);
               float a0, a1, a2, a3;
               gelu_erf_fast2(f2_fma(f2_pack(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1])), rs2,
-                                    f2_fma(f2_pack(cv[j].x, cv[j].y), nmr2, f2_pack(bv[j].x, bv[j].y))), a0, a1);
+                                    f2_fma(f2_pack(cq.x, cq.y), nmr2, f2_pack(bq.x, bq.y))), a0, a1);
               gelu_erf_fast2(f2_fma(f2_pack(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3])), rs2,
-                                    f2_fma(f2_pack(cv[j].z, cv[j].w), nmr2, f2_pack(bv[j].z, bv[j].w))), a2, a3);
+                                    f2_fma(f2_pack(cq.z, cq.w), nmr2, f2_pack(bq.z, bq.w))), a2, a3);
               pk[2 * j] = pack_bf16x2(a0, a1);
               pk[2 * j + 1] = pack_bf16x2(a2, a3);
             }
-            if (row_ok) {
-              uint32_t lo[8], hi[8];
+          }
+          if (!kDouble) {                            // the values are consumed: fetch the next chunk / free the accumulator
+            if (c + 1 < NC) tmem_ld32(t_acc + (c + 1) * 32, v[0]);
+            else release_acc(as);
+          }
+          if (nc < p.n && row_ok) {
+            uint32_t lo[8], hi[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
-              st_global_v8(crow + c * 32, lo);
-              st_global_v8(crow + c * 32 + 16, hi);
-            }
+            for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
+            st_global_v8(crow + c * 32, lo);
+            st_global_v8(crow + c * 32 + 16, hi);
           }
         }
       } else if constexpr (!kOutF32) {

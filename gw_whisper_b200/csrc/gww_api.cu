@@ -251,11 +251,11 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int max_groups = g_num_sms / MC;
   const int grid = (items < max_groups ? items : max_groups) * MC;
   if constexpr (MC == 1) {
-    kern<<<grid, kGemmThreads, GemmSmem<BN, MC>::kTotal, stream>>>(tmA, tmB, tmR, p);
+    kern<<<grid, gemm_threads<EPI, BN>(), GemmSmem<BN, MC>::kTotal, stream>>>(tmA, tmB, tmR, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(gemm_threads<EPI, BN>());
     cfg.dynamicSmemBytes = GemmSmem<BN, MC>::kTotal;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
