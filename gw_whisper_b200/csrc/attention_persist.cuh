@@ -31,7 +31,10 @@ struct AttnPersistParams {
   int n_items;    // n_qpairs * n_heads * det-windows
 };
 
-constexpr int kApStages = 3;
+#ifndef GWW_AP_STAGES
+#define GWW_AP_STAGES 3
+#endif
+constexpr int kApStages = GWW_AP_STAGES;   // K/V ring depth (each stage = one 16 KB K tile + one 16 KB V tile)
 // Exponentials are issued in groups of kApGroup; the arguments of group g depend (through a
 // multiply-by-zero FFMA) on the row-sum accumulator as it stands after group g - kApLookahead, so at most
 // kApGroup * kApLookahead MUFUs of a warp are queued at a time: the MIO queue of the sub-partition, which
