@@ -401,11 +401,11 @@ struct QAdapterDev {
 
 // conv3x3(1->16, pad 1) + ReLU + maxpool2 : spec [n,H,W] -> act1 [n,H/2,W/2,16] (NHWC)
 // CTA = 16x16 pooled pixels (32x32 conv pixels); one thread per pooled pixel, 16 channels.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 qadapter_conv1_kernel(const float* __restrict__ spec, float* __restrict__ act1, int H, int W,
                       const QAdapterDev ad) {
   __shared__ float tile[34][35];
-  __shared__ float ws[9 * 16 + 16];
+  __shared__ __align__(16) float ws[9 * 16 + 16];
   const long n = blockIdx.z;
   const int py0 = blockIdx.y * 16, px0 = blockIdx.x * 16;
   const float* src = spec + n * static_cast<long>(H) * W;
@@ -423,22 +423,56 @@ qadapter_conv1_kernel(const float* __restrict__ spec, float* __restrict__ act1, 
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) p[a][b] = tile[2 * ly + a][2 * lx + b];
+  // 4 conv pixels x 16 channels as packed fp32 channel PAIRS (FFMA2); the nine taps' weights are fetched as
+  // four 16-byte broadcasts per tap instead of one 4-byte shared load per multiply-add (r1: the scalar form was
+  // bound by those 576 loads per thread: 8.6 ms per MLGWSC step against ~3 ms of arithmetic).  Every
+  // accumulator still sees bias, then the taps in (ky, kx) order: bit-identical results.
+  // (two passes of 8 channels keep the kernel at <= 64 registers: four CTAs per SM hide the tile-load latency
+  //  that bounds this otherwise tiny kernel)
   float o[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    float best = 0.f;     // ReLU floor: max(relu(a), relu(b), ...) == max(0, a, b, ...)
+  for (int hc = 0; hc < 2; ++hc) {
+    uint64_t acc[4][4];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+    for (int cp = 0; cp < 4; ++cp) {
+      const uint64_t bv = f2_pack(ws[144 + 8 * hc + 2 * cp], ws[144 + 8 * hc + 2 * cp + 1]);
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        float acc = ws[144 + c];
+      for (int px = 0; px < 4; ++px) acc[px][cp] = bv;
+    }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) acc = fmaf(p[dy + ky][dx + kx], ws[(ky * 3 + kx) * 16 + c], acc);
-        best = fmaxf(best, acc);
+      for (int kx = 0; kx < 3; ++kx) {
+        uint64_t w2[4];
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[(ky * 3 + kx) * 16 + 8 * hc + 4 * c4]);
+          w2[2 * c4] = f2_pack(wv.x, wv.y);
+          w2[2 * c4 + 1] = f2_pack(wv.z, wv.w);
+        }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const float iv = p[dy + ky][dx + kx];
+            const uint64_t iv2 = f2_pack(iv, iv);
+#pragma unroll
+            for (int cp = 0; cp < 4; ++cp) acc[dy * 2 + dx][cp] = f2_fma(iv2, w2[cp], acc[dy * 2 + dx][cp]);
+          }
       }
-    o[c] = best;
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+      float b0 = 0.f, b1 = 0.f;     // ReLU floor: max(relu(a), relu(b), ...) == max(0, a, b, ...)
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float a0, a1;
+        f2_unpack(acc[px][cp], a0, a1);
+        b0 = fmaxf(b0, a0);
+        b1 = fmaxf(b1, a1);
+      }
+      o[8 * hc + 2 * cp] = b0;
+      o[8 * hc + 2 * cp + 1] = b1;
+    }
   }
   const int PH = H >> 1, PW = W >> 1;
   float4* dst = reinterpret_cast<float4*>(act1 + ((n * PH + (py0 + ly)) * static_cast<long>(PW) + (px0 + lx)) * 16);
