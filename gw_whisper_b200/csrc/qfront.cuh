@@ -680,35 +680,60 @@ __global__ void __launch_bounds__(256)
 qadapter_pool_kernel(const float* __restrict__ map, float* __restrict__ out_f32,
                      __nv_bfloat16* __restrict__ out_tm, long tm_stride_w, long tm_off, int H, int W,
                      int OF, int OT, int det, const QAdapterDev ad) {
-  extern __shared__ __align__(16) float pool_smem[];   // [OF][cols] pooled-in-frequency columns
+  // per-CTA tables: the bin ranges (same float expressions as before, evaluated once per row / column instead of
+  // once per output) and the <= 8 source columns this CTA's 128 output columns touch, staged in shared memory
+  __shared__ int2 frange[128];          // [OF <= 128] source rows [fs, fe) of output row f
+  __shared__ int2 trange[128];          // source columns [ts, te) of output column t0 + i
+  __shared__ float cols[128 * 9];       // map[:, c0 : c0 + nc], row pitch 9
   const long n = blockIdx.y;
   const int t0 = blockIdx.x * 128;
   const int t1 = min(OT, t0 + 128);
-  // source columns touched by output columns [t0, t1)
   const int c0 = static_cast<int>(floorf(static_cast<float>(t0 * W) / OT));
-  const int c1 = static_cast<int>(ceilf(static_cast<float>(t1 * W) / OT));
+  const int c1 = min(W, static_cast<int>(ceilf(static_cast<float>(t1 * W) / OT)));
   const int nc = c1 - c0;                               // <= 8 for W=128, OT=3000
   const float* src = map + n * static_cast<long>(H) * W;
   const float g = ad.gamma[det], be = ad.beta[det];
   float* out32 = out_f32 ? out_f32 + n * static_cast<long>(OF) * OT : nullptr;
   __nv_bfloat16* outtm = out_tm ? out_tm + (n * tm_stride_w + tm_off) * static_cast<long>(OT + 2) * OF : nullptr;
+  const bool staged = (OF <= 128 && H <= 128 && nc <= 9);
+  if (staged) {
+    for (int f = threadIdx.x; f < OF; f += 256)
+      frange[f] = make_int2(static_cast<int>(floorf(static_cast<float>(f * H) / OF)),
+                            static_cast<int>(ceilf(static_cast<float>((f + 1) * H) / OF)));
+    for (int i = threadIdx.x; i < t1 - t0; i += 256) {
+      const int t = t0 + i;
+      trange[i] = make_int2(static_cast<int>(floorf(static_cast<float>(t * W) / OT)),
+                            static_cast<int>(ceilf(static_cast<float>((t + 1) * W) / OT)));
+    }
+    for (int i = threadIdx.x; i < H * nc; i += 256) {
+      const int y = i / nc, x = i - y * nc;
+      cols[y * 9 + x] = __ldg(src + y * W + c0 + x);
+    }
+    __syncthreads();
+  }
   for (int idx = threadIdx.x; idx < OF * (t1 - t0); idx += 256) {
     const int tt = idx / OF, f = idx - tt * OF;          // f fastest: coalesced time-major stores
     const int t = t0 + tt;
-    const int fs = static_cast<int>(floorf(static_cast<float>(f * H) / OF));
-    const int fe = static_cast<int>(ceilf(static_cast<float>((f + 1) * H) / OF));
-    const int ts = static_cast<int>(floorf(static_cast<float>(t * W) / OT));
-    const int te = static_cast<int>(ceilf(static_cast<float>((t + 1) * W) / OT));
+    int fs, fe, ts, te;
     float sum = 0.f;
-    for (int y = fs; y < fe; ++y)
-      for (int x = ts; x < te; ++x) sum += __ldg(src + y * W + x);
+    if (staged) {
+      fs = frange[f].x; fe = frange[f].y; ts = trange[tt].x; te = trange[tt].y;
+      for (int y = fs; y < fe; ++y)
+        for (int x = ts; x < te; ++x) sum += cols[y * 9 + (x - c0)];
+    } else {
+      fs = static_cast<int>(floorf(static_cast<float>(f * H) / OF));
+      fe = static_cast<int>(ceilf(static_cast<float>((f + 1) * H) / OF));
+      ts = static_cast<int>(floorf(static_cast<float>(t * W) / OT));
+      te = static_cast<int>(ceilf(static_cast<float>((t + 1) * W) / OT));
+      for (int y = fs; y < fe; ++y)
+        for (int x = ts; x < te; ++x) sum += __ldg(src + y * W + x);
+    }
     float v = sum / static_cast<float>((fe - fs) * (te - ts));
     v = ad.scale * v + ad.bias;
     v = v * g + be;
     if (out32) out32[static_cast<long>(f) * OT + t] = v;
     if (outtm) outtm[static_cast<long>(t + 1) * OF + f] = __float2bfloat16(v);
   }
-  (void)nc; (void)pool_smem;
   if (outtm && blockIdx.x == 0) {
     for (int i = threadIdx.x; i < OF; i += 256) {
       outtm[i] = __float2bfloat16(0.f);
