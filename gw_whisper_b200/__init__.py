@@ -7,6 +7,7 @@ from .models import (  # noqa: F401
     one_channel_ligo_binary_classifier,
     glitch_one_channel_classifier,
 )
+from . import evaluate  # noqa: F401  (FAR / sensitive distance of a trigger list: MLGWSC-1/evaluate.py get_stats)
 from .qfrontend import (  # noqa: F401
     QScanB200, QTransformAdapter, GWWhisperClassifier, remove_softmax_from_classifier)
 
