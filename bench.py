@@ -11,6 +11,13 @@ strain (MLGWSC-1/inference.py:198-199), so  value = windows * (204/2048) / secon
 
 One JSON line on stdout (rank 0).  Under torchrun each rank searches its own time shard (weak
 scaling); the only collective is the all-gather of the small per-rank trigger lists.
+
+The same line carries two sub-records (skip with --no-extra):
+  "mlgwsc"        BASELINE.json configs[3]/[4]: the MLGWSC-1 search (QScan + Q-Adapter + whisper-tiny) over a
+                  one-hour, four-segment ragged stream, partitioned over the N ranks by sharding.plan_shards and
+                  merged by the trigger all-gather (strong scaling of a fixed job), with its own roofline /
+                  cpu_baseline and an in-bench check against a single-rank prefix run;
+  "glitch_small"  configs[2] (N=1 only): whisper-small, 512 glitch-shaped windows, argmax.
 """
 from __future__ import annotations
 
@@ -133,61 +140,214 @@ def build_mlgwsc_model(size: str, batch: int):
     return model, base
 
 
-def run_mlgwsc(args):
-    """Non-default workload (configs[3]): sliding 1 s windows over a resident synthetic segment through
-    the Q front end.  Same timing rules as the headline run; prints one JSON line."""
+# MLGWSC-1 stream of the `mlgwsc` sub-record: one hour of two-detector strain in four ragged segments
+# (BASELINE.json configs[3]; configs[4] is the same search over a month).  Lengths in samples (even, not
+# multiples of the 204-sample hop or of the 256-window batch): 1500.25 s, 1100.5 s, 700.125 s, 299.125 s.
+MLGWSC_SEGMENTS = (3072512, 2253824, 1433856, 612608)
+
+
+def mlgwsc_segments(dev, scale: float = 1.0):
+    """Synthetic whitened strain generated ON THE DEVICE, identical on every rank (seed 1234 + segment id), with a
+    loud sine-Gaussian every ~97 s so that trigger counts differ from shard to shard."""
+    import math
     import torch
-    from gw_whisper_b200 import _lib
+    segs = []
+    for i, n in enumerate(MLGWSC_SEGMENTS):
+        n = int(n * scale) & ~1
+        g = torch.Generator(device=dev).manual_seed(1234 + i)
+        x = torch.randn(2, n, generator=g, device=dev)
+        t = torch.arange(4096, device=dev) / 2048.0
+        for j, t0 in enumerate(range(20 * 2048, n - 8192, 97 * 2048 + 333)):
+            f0, tau, amp = 60.0 + 37.0 * (j % 9), 0.01 + 0.004 * (j % 5), 6.0 + 3.0 * (j % 4)
+            sg = amp * torch.exp(-(t - 1.0) ** 2 / (2 * tau ** 2)) * torch.sin(2 * math.pi * f0 * t)
+            x[0, t0:t0 + 4096] += sg
+            x[1, t0 + 12:t0 + 12 + 4096] += 0.8 * sg
+        segs.append(x)
+    return segs
 
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
-    lib = _lib.load()
-    nwin = args.batch
-    model, base = build_mlgwsc_model(args.model, 256)
+
+def mlgwsc_cpu_baseline(size: str, n_windows: int, threads: int):
+    """The reference's MLGWSC-1 forward on the host cores: restated ml4gw QScan + the reference's Q-Adapter CNN
+    structure + HF WhisperEncoder fp32 with unmerged DoRA + softmax-less head (oracle/)."""
+    import torch
+    from oracle import encoder as E, qscan as OQ
+    torch.set_num_threads(threads)
+    base = E.make_encoder(size, 0, spread=True)
+    enc = E.attach_dora(base, E.synthetic_dora(size, targets=("q_proj", "k_proj", "v_proj", "out_proj")))
+    torch.manual_seed(11)
+    adapter = OQ.QTransformAdapter(n_detectors=2).eval()
+    head = E.seeded_head(E.head_mlgwsc(base.config.d_model, 2, 2, softmax=False), seed=3, gain=3.0)
     g = torch.Generator().manual_seed(1234)
-    seg = torch.randn(2, 2048 + HOP * (nwin - 1), generator=g).to(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    x = torch.randn(n_windows, 2, 2048, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        feats = adapter(x)
+        reps = torch.cat([enc(feats[:, i]).last_hidden_state[:, -1, :] for i in range(2)], dim=1)
+        out = head(reps)
+    dt = time.perf_counter() - t0
+    return n_windows / dt, dt, float(out.mean())
 
-    def step():
-        flush.zero_()
-        return model.stream_search(seg, HOP, nwin, 0.5)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
+def mlgwsc_record(args, dev, rank, world, lib):
+    """`mlgwsc` sub-record of the JSON line: the MLGWSC-1 search (QScan + Q-Adapter +
+    whisper-tiny + DoRA + USR head) over the one-hour ragged stream, partitioned over the ranks by
+    `sharding.plan_shards` (whole 256-window batches, 1844-sample halo) and merged with the trigger all-gather
+    `sharding.gather_triggers` (NCCL): strong scaling of a fixed job.  Timed on the device, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from gw_whisper_b200 import _lib, sharding
+    from gw_whisper_b200 import remove_softmax_from_classifier
+
+    model, base = build_mlgwsc_model("tiny", 256)
+    remove_softmax_from_classifier(model)
+    segs = mlgwsc_segments(dev, args.mlgwsc_scale)
+    nws = [sharding.n_windows(int(s.shape[1]), HOP) for s in segs]
+    total_windows = sum(nws)
+    # threshold: 97th percentile of the scores of a 512-window prefix of segment 0 (same on every rank)
+    n_prefix = min(512, nws[0])
+    pre_scores, _, _ = model.stream_search(segs[0][:, :(n_prefix - 1) * HOP + 2048].contiguous(), HOP, n_prefix, 1e30)
+    thr = float(torch.quantile(pre_scores, 0.97))
+    _, pre_idx, pre_sc = model.stream_search(segs[0][:, :(n_prefix - 1) * HOP + 2048].contiguous(), HOP, n_prefix, thr)
+    group = None
+
+    def one_pass():
+        return sharding.sharded_search(model, segs, HOP, thr, rank, world, group, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    one_pass()                                             # warm-up (workspaces, tensor maps, NCCL buffers)
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.gww_launch_count()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    (t_seg, t_idx, t_sc), all_scores = one_pass()
     e1.record()
     torch.cuda.synchronize()
     launches = lib.gww_launch_count() - l0
     ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # correctness inside the bench: the merged list restricted to the prefix == the single-rank prefix run
+    sel = (t_seg == 0) & (t_idx < n_prefix)
+    ok = bool(torch.equal(t_idx[sel], pre_idx.to(torch.int64)) and torch.equal(t_sc[sel], pre_sc))
+    ok = ok and all(int(a.numel()) == n for a, n in zip(all_scores, nws))
+    if not ok:
+        raise RuntimeError("mlgwsc: merged sharded triggers differ from the single-rank prefix run")
+    plan = sharding.plan_shards(nws, world)
+    trig_per_rank = []
+    key = t_seg * (1 << 40) + t_idx
+    for r in range(world):
+        c = 0
+        for p in plan[r]:
+            lo, hi = p.segment * (1 << 40) + p.first_window, p.segment * (1 << 40) + p.first_window + p.n_windows
+            c += int(((key >= lo) & (key < hi)).sum())
+        trig_per_rank.append(c)
+    rec = None
+    del all_scores
+    # per-kernel-class timing of rank 0's shard (one more pass)
     nk = lib.gww_profile_num_kinds()
     ms_k = (C.c_double * nk)()
     cnt_k = (C.c_long * nk)()
     lib.gww_profile_begin()
-    for _ in range(args.steps):
-        step()
+    one_pass()
     torch.cuda.synchronize()
     _lib.check(lib.gww_profile_end(ms_k, cnt_k))
-    names = [lib.gww_profile_kind_name(i).decode() for i in range(nk)]
-    kernels = {nm: {"ms_per_step": ms_k[i] / args.steps, "launches_per_step": cnt_k[i] // args.steps}
-               for i, nm in enumerate(names) if cnt_k[i]}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        names = [lib.gww_profile_kind_name(i).decode() for i in range(nk)]
+        kernels = {nm: {"ms": ms_k[i], "launches": int(cnt_k[i])} for i, nm in enumerate(names) if cnt_k[i]}
+        cfg = base.config
+        fl = flops_per_detwin(cfg.d_model, cfg.encoder_layers, cfg.encoder_ffn_dim)
+        hbm_peak = 6650.0
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            hbm_peak = float(json.load(open(pk_path)).get("hbm_gbs", hbm_peak))
+        n_dw0 = 2 * sum(p.n_windows for p in plan[0])      # det-windows rank 0 processed in the profiled pass
+        fe = {}
+        for nm, bytes_per_dw in (("qscan", 2048 * 4 + 512 * 512 * 4), ("qadapter", 512 * 512 * 4 + 3002 * 80 * 2)):
+            if nm in kernels:
+                gbs = bytes_per_dw * n_dw0 / (kernels[nm]["ms"] * 1e-3) / 1e9
+                fe[nm] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                          "algorithmic_bytes_per_det_window": bytes_per_dw, "ms": kernels[nm]["ms"], "traffic": None}
+        dom = max(fe, key=lambda k: fe[k]["ms"]) if fe else None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            wps, dt, _ = mlgwsc_cpu_baseline("tiny", args.mlgwsc_ref_windows, threads)
+            cpu = {"value": wps * SEC_PER_WINDOW, "unit": "strain-s/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.mlgwsc_ref_windows} windows x 2 detectors in {dt:.1f} s: restated ml4gw QScan + Q-Adapter "
+                             "CNN + HF WhisperEncoder(tiny) fp32 + unmerged DoRA + head"}
+        rec = {"metric": "strain-seconds searched/sec", "value": total_windows * SEC_PER_WINDOW / (ms * 1e-3),
+               "unit": "strain-s/s", "n_gpus": world, "ms": ms, "scaling": "strong",
+               "config": {"workload": "MLGWSC-1 search: QScan + Q-Adapter + whisper-tiny + DoRA(q,k,v,out) + USR head over "
+                                      f"{sum(int(s.shape[1]) for s in segs) / FS:.1f} s of 2-detector strain in "
+                                      f"{len(segs)} ragged segments, 256-window batches",
+                          "windows": total_windows, "windows_per_segment": nws,
+                          "parallelism": f"sharding.plan_shards: whole batches, 1844-sample halo, dp{world}",
+                          "collective": "all-gather of per-rank trigger counts + padded (segment, window, score) lists, "
+                                        "all-reduce-as-gather of the per-window scores (sharding.gather_triggers / gather_scores)"},
+               "windows_per_s": total_windows / (ms * 1e-3), "threshold": thr,
+               "triggers": int(t_idx.numel()), "triggers_per_rank": trig_per_rank,
+               "prefix_check": "merged triggers == single-rank run on the first %d windows" % n_prefix,
+               "model_tflops": (fl["total"] + 1.286e9) * 2 * total_windows / (ms * 1e-3) / 1e12,
+               "gpu_launches_rank0": int(launches), "kernels_rank0": kernels,
+               "roofline": (dict(fe[dom], kernel=dom) if dom else None), "roofline_frontend": fe, "cpu_baseline": cpu}
+    return rec
+
+
+def glitch_record(args, dev, lib):
+    """`glitch_small` sub-record: BASELINE.json configs[2], whisper-small + 11-class head on 512 glitch-shaped
+    windows (one detector) per step; strain resident in HBM."""
+    import math
+    import torch
+    from gw_whisper_b200 import B200WhisperEncoder, glitch_one_channel_classifier
+    from gw_whisper_b200 import synthetic as S
+    B = 512
+    base = S.make_encoder("small", 0, spread=True)
+    enc = B200WhisperEncoder.from_hf(base, chunk=args.chunk)
+    model = glitch_one_channel_classifier(enc, num_classes=11)
+    S.seeded_head(model.classifier, seed=5, gain=3.0)
+    model.refresh()
+    g = torch.Generator().manual_seed(4321)
+    t = torch.arange(2048) / 2048.0
+    strain = torch.randn(B, 2048, generator=g)
+    A = 5 + 15 * torch.rand(B, 1, generator=g)
+    f0 = 30 + 470 * torch.rand(B, 1, generator=g)
+    tau = 0.002 + 0.048 * torch.rand(B, 1, generator=g)
+    t0 = 0.3 + 0.4 * torch.rand(B, 1, generator=g)
+    strain += A * torch.exp(-(t[None] - t0) ** 2 / (2 * tau ** 2)) * torch.sin(2 * math.pi * f0 * t[None])
+    strain = strain[:, None, :].to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    steps = max(1, min(args.steps, 2))
+
+    def step():
+        flush.zero_()
+        return model.forward_strain(strain).argmax(1)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
     cfg = base.config
     fl = flops_per_detwin(cfg.d_model, cfg.encoder_layers, cfg.encoder_ffn_dim)
-    line = {"metric": "strain-seconds searched/sec", "value": nwin * SEC_PER_WINDOW * args.steps / (ms * 1e-3),
-            "unit": "strain-s/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 encoder / f32 Q front end", "data": "synthetic",
-            "config": {"workload": f"MLGWSC-1: QScan + Q-Adapter + whisper-{args.model} + DoRA + softmax head, "
-                                   f"{nwin} sliding windows x 2 detectors per step, 256-window batches",
-                       "l2": "256 MiB buffer written between timed steps"},
-            "windows_per_s": nwin * args.steps / (ms * 1e-3),
-            "model_tflops": (fl["total"] + 1.286e9) * 2 * nwin * args.steps / (ms * 1e-3) / 1e12,
-            "gpu_launches": int(launches), "kernels": kernels}
-    print(json.dumps(line), flush=True)
+    return {"metric": "strain-seconds searched/sec", "value": B * SEC_PER_WINDOW / (ms * 1e-3), "unit": "strain-s/s",
+            "ms_per_step": ms, "steps": steps, "windows_per_s": B / (ms * 1e-3),
+            "model_tflops": fl["total"] * B / (ms * 1e-3) / 1e12,
+            "config": {"workload": "Glitch_classification: whisper-small + 11-class head, log-mel, 512 glitch-shaped "
+                                   "windows x 1 detector per step (argmax)", "det_windows_per_chunk": args.chunk}}
 
 
 def reference_windows_per_s(size: str, n_windows: int, threads: int):
@@ -423,6 +583,14 @@ def run_b200(args):
         cpu_baseline = {"value": wps * SEC_PER_WINDOW, "unit": "strain-s/s", "cores": threads, "kind": "port",
                         "sample": f"{args.ref_windows} windows x 2 detectors in {dt:.1f} s: scipy resample + HF "
                                   "WhisperFeatureExtractor + HF WhisperEncoder fp32 + unmerged DoRA + head"}
+    extras = {}
+    if not args.no_extra:
+        del model, dev_strain, flush
+        torch.cuda.empty_cache()
+        extras["mlgwsc"] = mlgwsc_record(args, dev, rank, world, lib)
+        if rank == 0 and world == 1:
+            torch.cuda.empty_cache()
+            extras["glitch_small"] = glitch_record(args, dev, lib)
     if rank == 0:
         line = {
             "metric": "strain-seconds searched/sec", "value": value, "unit": "strain-s/s", "n_gpus": world,
@@ -444,6 +612,7 @@ def run_b200(args):
             "gpu_launches": int(launches_per_run), "host_issue_ms_per_step": host_issue_ms,
             "roofline": roofline, "roofline_gemm": roofline_gemm, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -462,14 +631,11 @@ def main():
                          "front end and 96 attention work items per SM; measured 217.8 vs 222.5 ms per step for 256)")
     ap.add_argument("--ref-windows", type=int, default=40, help="windows per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="svn", choices=["svn", "mlgwsc"],
-                    help="svn = headline (configs[1]); mlgwsc = Q front end path (configs[3], 1 GPU, extra)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the mlgwsc (configs[3], sharded over the ranks) and glitch_small (configs[2]) sub-records")
+    ap.add_argument("--mlgwsc-scale", type=float, default=1.0, help="scale of the one-hour MLGWSC-1 stream (tests: 0.02)")
+    ap.add_argument("--mlgwsc-ref-windows", type=int, default=12, help="windows of the MLGWSC-1 CPU baseline sample")
     args = ap.parse_args()
-    if args.workload == "mlgwsc" and args.impl == "b200":
-        if args.model == "base":
-            args.model = "tiny"
-        run_mlgwsc(args)
-        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,8 +10,10 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# GWW_OPERAND=bf16 selects the bf16-operand build (default: fp16 operands, see include/gww.h gww_operand_dtype);
 # GWW_LIB overrides the library path (A/B builds of kernel variants for tuning runs)
-LIB_PATH = os.environ.get("GWW_LIB") or os.path.join(HERE, "libgww_b200.so")
+_VARIANT = "_bf16" if os.environ.get("GWW_OPERAND", "").lower() == "bf16" else ""
+LIB_PATH = os.environ.get("GWW_LIB") or os.path.join(HERE, f"libgww_b200{_VARIANT}.so")
 
 GWW_MAX_HEAD_LAYERS = 6
 c_float_p = C.POINTER(C.c_float)
@@ -57,12 +59,15 @@ _vp, _l, _i, _f, _sz = C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
     "gww_last_error": (C.c_char_p, []),
     "gww_version": (C.c_char_p, []),
+    "gww_operand_dtype": (C.c_char_p, []),
     "gww_device_ok": (_i, []),
     "gww_model_create": (_i, [C.POINTER(EncoderConfig), C.POINTER(EncoderWeights), C.POINTER(_vp)]),
     "gww_model_set_head": (_i, [_vp, C.POINTER(HeadWeights)]),
     "gww_model_destroy": (None, [_vp]),
     "gww_workspace_bytes": (_sz, [_vp, _i]),
     "gww_logmel_frontend": (_i, [_vp, _l, _vp, _vp]),
+    "gww_resample_16k": (_i, [_vp, _l, _vp, _vp]),
+    "gww_logmel_from_16k": (_i, [_vp, _l, _vp, _vp]),
     "gww_encoder_forward": (_i, [_vp, _vp, _l, _vp, _vp, _i, _vp, _sz, _i, _vp]),
     "gww_head_forward": (_i, [_vp, _vp, _l, _vp, _vp]),
     "gww_forward_windows_logmel": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp, _sz, _i, _vp]),
@@ -79,6 +84,8 @@ SYMBOLS = {
     "gww_forward_windows_qscan": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
     "gww_stream_search_qscan": (_i, [_vp, _vp, _vp, _i, _l, _i, _l, _l, _i, _f, _vp, _vp, _vp, _vp, _i,
                                      _vp, _sz, _vp, _sz, _vp]),
+    "gww_whiten_workspace_bytes": (_sz, [_l, _i, _i, _i, _i]),
+    "gww_whiten": (_i, [_vp, _l, C.c_double, _i, _i, _i, C.c_double, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gww_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _i, _i, _i, _vp]),
     "gww_attention": (_i, [_vp, _vp, _l, _i, _i, _vp]),
     "gww_layernorm": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _vp]),
@@ -109,6 +116,12 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def operand_dtype():
+    """torch dtype of the library's 16-bit tensor-core operands (torch.float16 or torch.bfloat16)."""
+    import torch
+    return torch.bfloat16 if load().gww_operand_dtype() == b"bf16" else torch.float16
 
 
 def check(rc: int) -> None:

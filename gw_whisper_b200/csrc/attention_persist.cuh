@@ -180,8 +180,8 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
       }
     } else if (warp == 9) {
       // ===================== MMA issuer (event driven, see attention_tc.cuh) =====================
-      constexpr uint32_t kIdescS = make_idesc_bf16(128, 128, 0);
-      constexpr uint32_t kIdescO = make_idesc_bf16(128, 64, 1);   // V is MN-major
+      constexpr uint32_t kIdescS = make_idesc_op16(128, 128, 0);
+      constexpr uint32_t kIdescO = make_idesc_op16(128, 64, 1);   // V is MN-major
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
       const uint32_t tS[2] = {tb + 0u, tb + 128u};
       const uint32_t tP[2] = {tb + 256u, tb + 320u};
@@ -371,7 +371,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
           l0 += p0;
           l1 += p1;
 #endif
-          pk[(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          pk[(c & 1) * 16 + (i >> 1)] = pack_op16x2(p0, p1);
         }
         if (c & 1) {                                 // 64 keys packed -> 32 TMEM columns of P: half c >> 1
           if (!pv_waited) {
@@ -426,7 +426,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
           const int col = jc * 8 + e * 2;
           const float a0 = __uint_as_float(col < 32 ? o0[col & 31] : o1[col & 31]) * inv_l;
           const float a1 = __uint_as_float(col < 32 ? o0[(col + 1) & 31] : o1[(col + 1) & 31]) * inv_l;
-          pk[e] = pack_bf16x2(a0, a1);
+          pk[e] = pack_op16x2(a0, a1);
         }
         *reinterpret_cast<uint4*>(sb + ((jc ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }

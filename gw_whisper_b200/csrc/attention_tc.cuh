@@ -188,8 +188,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
       }
     } else if (warp == kMmaWarp) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t kIdescS = make_idesc_bf16(128, 128, 0);
-      constexpr uint32_t kIdescO = make_idesc_bf16(128, 64, 1);   // V is MN-major
+      constexpr uint32_t kIdescS = make_idesc_op16(128, 128, 0);
+      constexpr uint32_t kIdescO = make_idesc_op16(128, 64, 1);   // V is MN-major
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
       // TMEM map: S_t at t*128, P_t at NT*128 + t*64, O_t at NT*192 + t*64  (second entries unused for NT = 1)
       const uint32_t tS[2] = {tb + 0u, tb + 128u};
@@ -406,7 +406,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
             l0 += p0;
             l1 += p1;
           }
-          pk[(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+          pk[(c & 1) * 16 + (i >> 1)] = pack_op16x2(p0, p1);
         }
         if (c & 1) {                                 // 64 columns packed -> 32 TMEM columns of P
           if (!pv_waited) {
@@ -445,7 +445,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, Bt} b
         const int col = jc * 8 + e * 2;
         const float a0 = __uint_as_float(col < 32 ? o0[col & 31] : o1[col & 31]) * inv_l;
         const float a1 = __uint_as_float(col < 32 ? o0[(col + 1) & 31] : o1[(col + 1) & 31]) * inv_l;
-        pk[e] = pack_bf16x2(a0, a1);
+        pk[e] = pack_op16x2(a0, a1);
       }
       *reinterpret_cast<uint4*>(sb + ((jc ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }

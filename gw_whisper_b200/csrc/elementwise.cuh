@@ -48,7 +48,7 @@ layernorm_kernel(const float* __restrict__ in, OutT* __restrict__ out,
     const float o0 = fmaf(v[i].x * rstd, g.x, b.x), o1 = fmaf(v[i].y * rstd, g.y, b.y);
     const float o2 = fmaf(v[i].z * rstd, g.z, b.z), o3 = fmaf(v[i].w * rstd, g.w, b.w);
     if constexpr (sizeof(OutT) == 2) {
-      uint2 pk = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      uint2 pk = make_uint2(pack_op16x2(o0, o1), pack_op16x2(o2, o3));
       reinterpret_cast<uint2*>(out + row * D)[lane + 32 * i] = pk;
     } else {
       reinterpret_cast<float4*>(out + row * D)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
@@ -76,7 +76,7 @@ mean_pool_kernel(const float* __restrict__ hs, float* __restrict__ out, int T, i
 // modeling_whisper.py:215-238 for that one row, in fp32 on CUDA cores (1500 x 64 MACs per head).
 //   qkv [nc, T, 3d] bf16 (q pre-scaled) -> out [nc, d] bf16 ; grid (heads, nc), 256 threads
 __global__ void __launch_bounds__(256)
-last_row_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
+last_row_attention_kernel(const op16_t* __restrict__ qkv, op16_t* __restrict__ out, int T,
                           int d) {
   extern __shared__ __align__(16) float lra_smem[];   // [T] scores | [8][64] partial outputs | [16] reductions
   float* sc = lra_smem;
@@ -85,17 +85,17 @@ last_row_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
   const int h = blockIdx.x;
   const long b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* base = qkv + b * static_cast<long>(T) * 3 * d + h * 64 + 2 * lane;
-  const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + static_cast<long>(T - 1) * 3 * d));
-  const __nv_bfloat16* kb = base + d;
-  const __nv_bfloat16* vb = base + 2 * d;
+  const op16_t* base = qkv + b * static_cast<long>(T) * 3 * d + h * 64 + 2 * lane;
+  const float2 q = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(base + static_cast<long>(T - 1) * 3 * d));
+  const op16_t* kb = base + d;
+  const op16_t* vb = base + 2 * d;
   float wmax = -INFINITY;
   for (int k0 = warp * 4; k0 < T; k0 += 32) {        // 4 keys per warp iteration: 4 loads in flight
     float dot[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int k = min(k0 + u, T - 1);
-      const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kb + static_cast<long>(k) * 3 * d));
+      const float2 kv = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(kb + static_cast<long>(k) * 3 * d));
       dot[u] = q.x * kv.x + q.y * kv.y;
     }
 #pragma unroll
@@ -133,7 +133,7 @@ last_row_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
     for (int u = 0; u < 4; ++u) {
       const int k = min(k0 + u, T - 1);
       const float pk = (k0 + u < T) ? sc[k] : 0.f;
-      const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + static_cast<long>(k) * 3 * d));
+      const float2 vv = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(vb + static_cast<long>(k) * 3 * d));
       acc.x = fmaf(pk, vv.x, acc.x);
       acc.y = fmaf(pk, vv.y, acc.y);
     }
@@ -145,7 +145,7 @@ last_row_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v += part[i * 64 + threadIdx.x];
-    out[b * d + h * 64 + threadIdx.x] = __float2bfloat16(v / tot);
+    out[b * d + h * 64 + threadIdx.x] = float_to_op16(v / tot);
   }
 }
 

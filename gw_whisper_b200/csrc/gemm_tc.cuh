@@ -54,7 +54,7 @@ struct GemmParams {
   unsigned long long magic_tiles_n;
   unsigned long long magic_tiles_per_batch;
   // ---- LayerNorm folding (see "LayerNorm folding" below).  Producer side (f32-output epilogues):
-  __nv_bfloat16* xb;     // bf16 copy of the output rows [batch*rows, n] (the next GEMM's A operand) or nullptr
+  op16_t* xb;     // bf16 copy of the output rows [batch*rows, n] (the next GEMM's A operand) or nullptr
   float* stats_out;      // per-row partial (sum, sum of squares): [batch*rows][stat_slots][2], slot = 2*n_tile + half
   // consumer side (bf16-output epilogues): out = rs * acc - rs * mu * c1[n] + c2[n], c2 passed as `bias`
   const float* stats_in; // the producer's partials for the rows of A, or nullptr (plain bias epilogue)
@@ -162,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kStages = S::kStages;
   constexpr bool kOutF32 = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32);
   constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128 * MC, BN, 0);
+  constexpr uint32_t kIdesc = make_idesc_op16(128 * MC, BN, 0);
   constexpr uint16_t kPairMask = 0x3;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -388,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (EPI == EPI_BIAS_GELU_BF16) {
         // GELU epilogues are issue-bound (measured: staging costs them 6 %): straight 256-bit stores
         const bool row_ok = lane < rows_here;
-        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
+        op16_t* crow = reinterpret_cast<op16_t*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
                               static_cast<size_t>(row_ok ? rbase + lane : 0) * p.c_row_stride + n0;
         constexpr bool kDouble = (kEpiWarps == 8);   // 8 warps: next chunk's TMEM load in flight; 16: other warps hide it
         tmem_ld32(t_acc, v[0]);
@@ -412,8 +412,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     f2_fma(f2_pack(cq.x, cq.y), nmr2, f2_pack(bq.x, bq.y))), a0, a1);
               gelu_erf_fast2(f2_fma(f2_pack(__uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3])), rs2,
                                     f2_fma(f2_pack(cq.z, cq.w), nmr2, f2_pack(bq.z, bq.w))), a2, a3);
-              pk[2 * j] = pack_bf16x2(a0, a1);
-              pk[2 * j + 1] = pack_bf16x2(a2, a3);
+              pk[2 * j] = pack_op16x2(a0, a1);
+              pk[2 * j + 1] = pack_op16x2(a2, a3);
             }
           }
           if (!kDouble) {                            // the values are consumed: fetch the next chunk / free the accumulator
@@ -429,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else if constexpr (!kOutF32) {
-        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
+        op16_t* cb = reinterpret_cast<op16_t*>(p.c) + static_cast<size_t>(b) * p.c_batch_stride +
                             static_cast<size_t>(rbase) * p.c_row_stride + n0;
         // move `ncols` (32 or 64) staged bf16 columns starting at column `col0` of the warp's range:
         // all shared loads first, then the stores (independent registers: the accesses overlap)
@@ -442,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int row = 4 * ps + srow;
               d[ps] = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sslot ^ (row & 7)) << 4));
             }
-            __nv_bfloat16* dst = cb + static_cast<size_t>(srow) * p.c_row_stride + col0 + 8 * sslot;
+            op16_t* dst = cb + static_cast<size_t>(srow) * p.c_row_stride + col0 + 8 * sslot;
 #pragma unroll
             for (int ps = 0; ps < 8; ++ps) {
               if (4 * ps + srow < rows_here) *reinterpret_cast<uint4*>(dst) = d[ps];
@@ -456,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int row = 8 * ps + r8;
               d[ps] = *reinterpret_cast<const uint4*>(stg + row * 128 + ((sl ^ (row & 7)) << 4));
             }
-            __nv_bfloat16* dst = cb + static_cast<size_t>(r8) * p.c_row_stride + col0 + 8 * sl;
+            op16_t* dst = cb + static_cast<size_t>(r8) * p.c_row_stride + col0 + 8 * sl;
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
               if (8 * ps + r8 < rows_here) *reinterpret_cast<uint4*>(dst) = d[ps];
@@ -498,8 +498,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                  f2_fma(f2_pack(cq.x, cq.y), nmr2, f2_pack(bq.x, bq.y))), a0, a1);
                 f2_unpack(f2_fma(f2_pack(__uint_as_float(vc[8 * j + 4 * h + 2]), __uint_as_float(vc[8 * j + 4 * h + 3])), rs2,
                                  f2_fma(f2_pack(cq.z, cq.w), nmr2, f2_pack(bq.z, bq.w))), a2, a3);
-                pk[2 * h] = pack_bf16x2(a0, a1);
-                pk[2 * h + 1] = pack_bf16x2(a2, a3);
+                pk[2 * h] = pack_op16x2(a0, a1);
+                pk[2 * h + 1] = pack_op16x2(a2, a3);
               }
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_row + (((hslot + j) ^ (lane & 7)) << 4)),
                            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -531,7 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int ps = 0; ps < 8; ++ps) { dst[ps].x += bq.x; dst[ps].y += bq.y; dst[ps].z += bq.z; dst[ps].w += bq.w; }
           }
         };
-        __nv_bfloat16* xbp = (p.xb != nullptr)
+        op16_t* xbp = (p.xb != nullptr)
                                  ? p.xb + (static_cast<size_t>(b) * p.rows + rbase + srow) * p.n + n0 + 4 * sslot
                                  : nullptr;
         float rsum[8], rsq[8];
@@ -584,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               dst += 4 * p.c_row_stride;
               if (xbp != nullptr) {
                 if (rok) *reinterpret_cast<uint2*>(xbp + static_cast<size_t>(4 * (4 * g4 + k)) * p.n + c * 32) =
-                    make_uint2(pack_bf16x2(d[k].x, d[k].y), pack_bf16x2(d[k].z, d[k].w));
+                    make_uint2(pack_op16x2(d[k].x, d[k].y), pack_op16x2(d[k].z, d[k].w));
                 rsum[4 * g4 + k] += (d[k].x + d[k].y) + (d[k].z + d[k].w);
                 rsq[4 * g4 + k] += fmaf(d[k].x, d[k].x, d[k].y * d[k].y) + fmaf(d[k].z, d[k].z, d[k].w * d[k].w);
               }

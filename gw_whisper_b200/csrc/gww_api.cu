@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -18,6 +19,7 @@
 #include "gemm_tc.cuh"
 #include "logmel.cuh"
 #include "qfront.cuh"
+#include "whiten.cuh"
 
 using namespace gww;
 
@@ -55,14 +57,25 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* gww_last_error(void) { return g_err.c_str(); }
-extern "C" const char* gww_version(void) { return "gw-whisper-b200 0.1 (sm_100a)"; }
+extern "C" const char* gww_version(void) { return "gw-whisper-b200 0.2 (sm_100a, " GWW_OPERAND_NAME " operands)"; }
+extern "C" const char* gww_operand_dtype(void) { return GWW_OPERAND_NAME; }
 extern "C" long gww_launch_count(void) { return g_launches.load(); }
 
-static int g_num_sms = 0;
+// Process-global state is keyed by the device ordinal (a process may drive more than one GPU) and guarded
+// by g_state_mu where it is mutated after start-up.
+constexpr int kMaxDevices = 64;
+static int g_sms_by_dev[kMaxDevices] = {0};
+static std::mutex g_state_mu;
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+#define g_num_sms (g_sms_by_dev[current_device()])
 static std::atomic<int> g_prune_last{1};
 extern "C" int gww_set_last_layer_pruning(int enable) { return g_prune_last.exchange(enable ? 1 : 0); }
 extern "C" int gww_device_ok(void) {
-  if (g_num_sms > 0) return GWW_OK;   // one process per GPU: checked once
+  if (g_num_sms > 0) return GWW_OK;   // checked once per device
   int dev = 0, count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
     cudaGetLastError();
@@ -74,7 +87,21 @@ extern "C" int gww_device_ok(void) {
   if (prop.major != 10)
     return fail(GWW_ERR_NO_DEVICE, "device %s is sm_%d%d; kernels are built for sm_100a only",
                 prop.name, prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
+  if (dev < 0 || dev >= kMaxDevices) return fail(GWW_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
+  g_sms_by_dev[dev] = prop.multiProcessorCount;
+  return GWW_OK;
+}
+
+// cudaFuncSetAttribute is per (function, device): remember which pairs were already opted in.
+static std::unordered_map<uint64_t, int> g_attr_done;
+template <typename K>
+static int ensure_smem_attr(K kern, int bytes) {
+  const uint64_t key = (uint64_t)(uintptr_t)reinterpret_cast<const void*>(kern) * 64ull + (uint64_t)current_device();
+  std::lock_guard<std::mutex> lk(g_state_mu);
+  auto it = g_attr_done.find(key);
+  if (it != g_attr_done.end() && it->second >= bytes) return GWW_OK;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  g_attr_done[key] = bytes;
   return GWW_OK;
 }
 
@@ -84,27 +111,36 @@ extern "C" int gww_device_ok(void) {
 // ------------------------------------------------------------------------------------------------
 enum ProfKind : int {
   PK_LOGMEL = 0, PK_FEATS_TM, PK_GEMM_CONV1, PK_GEMM_CONV2, PK_LN, PK_GEMM_QKV, PK_ATTN, PK_GEMM_O,
-  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_ATTN_LAST, PK_COUNT
+  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_ATTN_LAST, PK_WHITEN, PK_COUNT
 };
 static const char* kProfNames[PK_COUNT] = {"logmel", "feats_to_timemajor", "gemm_conv1", "gemm_conv2",
                                            "layernorm", "gemm_qkv", "attention", "gemm_out_proj",
                                            "gemm_fc1", "gemm_fc2", "head", "other", "qscan", "qadapter",
-                                           "attention_last_row"};
+                                           "attention_last_row", "whiten"};
 struct ProfRec { cudaEvent_t a, b; int kind; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof_recs;
+// The profiler is a single-device, single-thread diagnostic (bench.py): records are kept in a deque so that
+// pointers stay valid while it grows, the bookkeeping is under g_prof_mu, and records made on another device
+// than the one gww_profile_begin() ran on are skipped.
+static std::atomic<bool> g_prof_on{false};
+static std::deque<ProfRec> g_prof_recs;
 static size_t g_prof_used = 0;
+static int g_prof_dev = 0;
+static std::mutex g_prof_mu;
 struct ProfScope {
   ProfRec* r = nullptr;
   cudaStream_t s;
   ProfScope(int kind, cudaStream_t stream) : s(stream) {
-    if (!g_prof_on) return;
-    if (g_prof_used == g_prof_recs.size()) {
-      ProfRec n{};
-      if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
-      g_prof_recs.push_back(n);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    {
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      if (current_device() != g_prof_dev) return;
+      if (g_prof_used == g_prof_recs.size()) {
+        ProfRec n{};
+        if (cudaEventCreate(&n.a) != cudaSuccess || cudaEventCreate(&n.b) != cudaSuccess) return;
+        g_prof_recs.push_back(n);
+      }
+      r = &g_prof_recs[g_prof_used++];
     }
-    r = &g_prof_recs[g_prof_used++];
     r->kind = kind;
     cudaEventRecord(r->a, s);
   }
@@ -112,10 +148,17 @@ struct ProfScope {
 };
 extern "C" int gww_profile_num_kinds(void) { return PK_COUNT; }
 extern "C" const char* gww_profile_kind_name(int k) { return (k >= 0 && k < PK_COUNT) ? kProfNames[k] : ""; }
-extern "C" int gww_profile_begin(void) { g_prof_used = 0; g_prof_on = true; return GWW_OK; }
+extern "C" int gww_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_used = 0;
+  g_prof_dev = current_device();
+  g_prof_on = true;
+  return GWW_OK;
+}
 // Stops profiling, waits for the recorded events and accumulates milliseconds / launch counts.
 extern "C" int gww_profile_end(double* ms_by_kind, long* count_by_kind) {
   g_prof_on = false;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (int k = 0; k < PK_COUNT; ++k) { ms_by_kind[k] = 0.0; count_by_kind[k] = 0; }
   for (size_t i = 0; i < g_prof_used; ++i) {
     ProfRec& r = g_prof_recs[i];
@@ -194,7 +237,8 @@ static int make_map_uncached(CUtensorMap* m, bool f32, int rank, const void* bas
     es[i] = 1;
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                            : (GWW_OPERAND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16),
                         rank, const_cast<void*>(base), gdim, gstr, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -239,13 +283,8 @@ struct GemmCall {
 template <int BN, int EPI, int MC>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR,
                          const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, EPI, MC>;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN, MC>::kTotal));
-    attr_set = true;
-  }
+  GWW_TRY(ensure_smem_attr(kern, GemmSmem<BN, MC>::kTotal));
   const int tiles_m = ((p.rows + 127) / 128) * p.batch;
   const int items = ((tiles_m + MC - 1) / MC) * ((p.n + BN - 1) / BN);
   const int max_groups = g_num_sms / MC;
@@ -358,7 +397,7 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
 // plain Linear: C[M,N] = epi(A[M,K] W[N,K]^T)
 // LayerNorm-fold plumbing of one Linear: producer side (writes xb + stats) or consumer side (reads them)
 struct LnFold {
-  __nv_bfloat16* xb = nullptr;
+  op16_t* xb = nullptr;
   float* stats_out = nullptr;
   const float* stats_in = nullptr;
   const float* c1 = nullptr;
@@ -413,12 +452,8 @@ static int pick_block_n(int n) {
 template <int NT>
 static int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmO, const AttnParams& ap, long n, int T, int d,
                             cudaStream_t stream) {
-  static bool attr_set = false;
   auto kern = attention_tc_kernel<NT>;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<NT>::kSmemBytes));
-    attr_set = true;
-  }
+  GWW_TRY(ensure_smem_attr(kern, AttnCfg<NT>::kSmemBytes));
   if (n > 32768) return fail(GWW_ERR_INVALID, "attention: more than 32768 det-windows per call");   // gridDim.z limit
   dim3 grid((T + 128 * NT - 1) / (128 * NT), d / 64, (unsigned)n);
   ProfScope ps(PK_ATTN, stream);
@@ -459,11 +494,7 @@ static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaS
   const uint32_t ob[3] = {64, 32, 1};
   GWW_TRY(make_map(&tmO, false, 3, out, od, os, ob));
   if (attention_persistent()) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CU_TRY(cudaFuncSetAttribute(attention_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBytes));
-      attr_set = true;
-    }
+    GWW_TRY(ensure_smem_attr(attention_persist_kernel, kApSmemBytes));
     AttnPersistParams pp;
     pp.T = T; pp.d_model = d; pp.nkv = (T + 127) / 128; pp.n_heads = d / 64; pp.n_qpairs = (T + 255) / 256;
     const long items = (long)pp.n_qpairs * pp.n_heads * n;
@@ -502,9 +533,11 @@ static int run_ln_t(const float* x, OutT* out, const float* g, const float* b, l
 // ------------------------------------------------------------------------------------------------
 // log-mel tables
 // ------------------------------------------------------------------------------------------------
-static LogmelTables g_lm{};
-static bool g_lm_ready = false;
+static LogmelTables g_lm_by_dev[kMaxDevices]{};
+static bool g_lm_ready_by_dev[kMaxDevices] = {false};
 static std::mutex g_lm_mu;
+#define g_lm (g_lm_by_dev[current_device()])
+#define g_lm_ready (g_lm_ready_by_dev[current_device()])
 
 static double hz_to_mel(double f) {
   return (f >= 1000.0) ? 15.0 + std::log(f / 1000.0) * (27.0 / std::log(6.4)) : 3.0 * f / 200.0;
@@ -563,7 +596,7 @@ static int logmel_tables_init() {
   GWW_TRY(upload(cnt, &g_lm.mel_cnt));
   GWW_TRY(upload(off, &g_lm.mel_off));
   GWW_TRY(upload(wts, &g_lm.mel_w));
-  CU_TRY(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmSmemBytes));
+  GWW_TRY(ensure_smem_attr(logmel_kernel, kLmSmemBytes));
   g_lm_ready = true;
   return GWW_OK;
 }
@@ -584,12 +617,12 @@ gather_windows_kernel(const float* __restrict__ strain, float* __restrict__ out,
   for (int i = threadIdx.x; i < 2048; i += 256) out[w * 2048 + i] = src[i];
 }
 
-static int run_logmel(const float* strain_contig, long n, float* out_f32, __nv_bfloat16* out_tm,
-                      cudaStream_t stream) {
+static int run_logmel(const float* strain_contig, long n, float* out_f32, op16_t* out_tm,
+                      cudaStream_t stream, const float* audio_in = nullptr, float* audio_out = nullptr) {
   GWW_TRY(logmel_tables_init());
   const int grid = (int)(n < (long)g_num_sms ? n : (long)g_num_sms);
   ProfScope ps(PK_LOGMEL, stream);
-  logmel_kernel<<<grid, kLmThreads, kLmSmemBytes, stream>>>(strain_contig, n, out_f32, out_tm, g_lm);
+  logmel_kernel<<<grid, kLmThreads, kLmSmemBytes, stream>>>(strain_contig, n, out_f32, out_tm, g_lm, audio_in, audio_out);
   LAUNCH_CHECK();
   return GWW_OK;
 }
@@ -599,19 +632,20 @@ static int run_logmel(const float* strain_contig, long n, float* out_f32, __nv_b
 // ------------------------------------------------------------------------------------------------
 struct LayerDev {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
+  op16_t *qkv_w, *o_w, *fc1_w, *fc2_w;
   float *qkv_b, *o_b, *fc1_b, *fc2_b;
   // LayerNorm folded into the consuming Linear (gemm_tc.cuh "LayerNorm folding"): W (.) gamma in bf16,
   // c1[n] = sum_k of those bf16 weights, c2[n] = sum_k beta_k W_nk + b_n
-  __nv_bfloat16 *qkv_wf, *fc1_wf;
+  op16_t *qkv_wf, *fc1_wf;
   float *qkv_c1, *qkv_c2, *fc1_c1, *fc1_c2;
 };
 struct gww_model {
   gww_encoder_config_t cfg;
-  __nv_bfloat16 *conv1_w, *conv2_w;   // [d, 384], [d, 3d]
+  op16_t *conv1_w, *conv2_w;   // [d, 384], [d, 3d]
   float *conv1_b, *conv2_b, *pos_emb, *lnp_g, *lnp_b;
   std::vector<LayerDev> layers;
   std::vector<void*> owned;
+  std::vector<void*> head_owned;   // device buffers of the current head (freed when the head is replaced)
   bool has_head = false;
   HeadParams head{};
   float* head_scratch = nullptr;   // 2 x rows x kHeadMaxWidth ping-pong activations
@@ -627,13 +661,13 @@ static int dev_f32(gww_model* m, const float* h, size_t n, float** out) {
   *out = d;
   return GWW_OK;
 }
-static int dev_bf16(gww_model* m, const std::vector<float>& h, __nv_bfloat16** out) {
-  std::vector<__nv_bfloat16> hb(h.size());
-  for (size_t i = 0; i < h.size(); ++i) hb[i] = __float2bfloat16(h[i]);
-  __nv_bfloat16* d = nullptr;
-  CU_TRY(cudaMalloc(&d, hb.size() * sizeof(__nv_bfloat16)));
+static int dev_bf16(gww_model* m, const std::vector<float>& h, op16_t** out) {
+  std::vector<op16_t> hb(h.size());
+  for (size_t i = 0; i < h.size(); ++i) hb[i] = float_to_op16(h[i]);
+  op16_t* d = nullptr;
+  CU_TRY(cudaMalloc(&d, hb.size() * sizeof(op16_t)));
   m->owned.push_back(d);
-  CU_TRY(cudaMemcpy(d, hb.data(), hb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(d, hb.data(), hb.size() * sizeof(op16_t), cudaMemcpyHostToDevice));
   *out = d;
   return GWW_OK;
 }
@@ -667,7 +701,7 @@ static void ln_fold(const std::vector<float>& W, const float* b, const float* ga
     for (int k = 0; k < K; ++k) {
       const float wg = W[(size_t)n * K + k] * gamma[k];
       Wf[(size_t)n * K + k] = wg;
-      s1 += (double)__bfloat162float(__float2bfloat16(wg));   // the sum of what the tensor core will multiply by
+      s1 += (double)op16_to_float(float_to_op16(wg));   // the sum of what the tensor core will multiply by
       s2 += (double)beta[k] * (double)W[(size_t)n * K + k];
     }
     c1[n] = (float)s1;
@@ -769,15 +803,25 @@ extern "C" int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* h) {
       return fail(GWW_ERR_INVALID, "set_head: layer width %d out of range", h->dims[i]);
     hp.dims[i] = h->dims[i];
   }
+  // replace, not accumulate: two classifiers alternating on one encoder must not leak a head per switch.
+  // cudaFree waits for in-flight work that still reads the old buffers.
+  for (void* p : m->head_owned) cudaFree(p);
+  m->head_owned.clear();
+  m->has_head = false;
   for (int i = 0; i < h->n_layers; ++i) {
-    float *dw, *db;
-    GWW_TRY(dev_f32(m, h->w[i], (size_t)h->dims[i] * h->dims[i + 1], &dw));
-    GWW_TRY(dev_f32(m, h->b[i], h->dims[i + 1], &db));
+    if (!h->w[i] || !h->b[i]) return fail(GWW_ERR_INVALID, "set_head: null weight pointer in layer %d", i);
+    float *dw = nullptr, *db = nullptr;
+    const size_t nw = (size_t)h->dims[i] * h->dims[i + 1], nb = (size_t)h->dims[i + 1];
+    CU_TRY(cudaMalloc(&dw, nw * sizeof(float)));
+    m->head_owned.push_back(dw);
+    CU_TRY(cudaMalloc(&db, nb * sizeof(float)));
+    m->head_owned.push_back(db);
+    CU_TRY(cudaMemcpy(dw, h->w[i], nw * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(db, h->b[i], nb * sizeof(float), cudaMemcpyHostToDevice));
     hp.w[i] = dw;
     hp.b[i] = db;
   }
-  CU_TRY(cudaFuncSetAttribute(head_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              kHeadWin * kHeadMaxWidth * 4));
+  GWW_TRY(ensure_smem_attr(head_linear_kernel, kHeadWin * kHeadMaxWidth * 4));
   m->head = hp;
   m->has_head = true;
   return GWW_OK;
@@ -786,6 +830,7 @@ extern "C" int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* h) {
 extern "C" void gww_model_destroy(gww_model_t* m) {
   if (!m) return;
   for (void* p : m->owned) cudaFree(p);
+  for (void* p : m->head_owned) cudaFree(p);
   if (m->head_scratch) cudaFree(m->head_scratch);
   delete m;
 }
@@ -794,16 +839,16 @@ extern "C" void gww_model_destroy(gww_model_t* m) {
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct Workspace {
-  __nv_bfloat16* feats_tm;  // [chunk, 3002, 80]
+  op16_t* feats_tm;  // [chunk, 3002, 80]
   float* x;                 // [chunk*1500, d]  residual stream
-  __nv_bfloat16* h;         // [chunk*1500, d]  LN output / attention output
-  __nv_bfloat16* g;         // [chunk*1500, ffn] fc1 output; aliases qkv [.,3d] and conv1 out [chunk,3001,d]
+  op16_t* h;         // [chunk*1500, d]  LN output / attention output
+  op16_t* g;         // [chunk*1500, ffn] fc1 output; aliases qkv [.,3d] and conv1 out [chunk,3001,d]
   float* pooled;            // [chunk, d]
   float* head_out;          // [chunk, 64]
   float* head_scratch;      // [2, chunk, kHeadMaxWidth]
   float* gather;            // [chunk, 2048] contiguous strain windows
   float* x_last;            // [chunk, d] residual rows of the last token (pruned final layer)
-  __nv_bfloat16* xb;        // [chunk*1500, d]  bf16 copy of the residual stream (LayerNorm fold: A operand of qkv / fc1)
+  op16_t* xb;        // [chunk*1500, d]  bf16 copy of the residual stream (LayerNorm fold: A operand of qkv / fc1)
   float* stats;             // [chunk*1500, kStatSlots, 2] per-row partial (sum, sum of squares) of x
   size_t total;
 };
@@ -814,21 +859,21 @@ static Workspace carve(const gww_model* m, int chunk, uint8_t* base) {
   Workspace w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base + o; };
-  w.feats_tm = (__nv_bfloat16*)take((size_t)chunk * 3002 * 80 * 2);
+  w.feats_tm = (op16_t*)take((size_t)chunk * 3002 * 80 * 2);
   w.x = (float*)take(M * d * 4);
-  w.h = (__nv_bfloat16*)take(M * d * 2);
+  w.h = (op16_t*)take(M * d * 2);
   size_t gbytes = M * f * 2;
   const size_t h1bytes = ((size_t)chunk * 3001 + 2) * d * 2;
   if (h1bytes > gbytes) gbytes = h1bytes;
   if (M * 3 * d * 2 > gbytes) gbytes = M * 3 * d * 2;
   if (M * d * 4 > gbytes) gbytes = M * d * 4;
-  w.g = (__nv_bfloat16*)take(gbytes);
+  w.g = (op16_t*)take(gbytes);
   w.pooled = (float*)take((size_t)chunk * d * 4);
   w.head_out = (float*)take((size_t)chunk * 64 * 4);
   w.head_scratch = (float*)take((size_t)2 * chunk * kHeadMaxWidth * 4);
   w.gather = (float*)take((size_t)chunk * 2048 * 4);
   w.x_last = (float*)take((size_t)chunk * d * 4);
-  w.xb = (__nv_bfloat16*)take(M * d * 2);
+  w.xb = (op16_t*)take(M * d * 2);
   w.stats = (float*)take(M * kStatSlots * 2 * 4);
   w.total = off;
   return w;
@@ -865,7 +910,7 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
   auto consume = [&](const float* c1, int slots) {
     LnFold lf; lf.stats_in = ws.stats; lf.c1 = c1; lf.in_slots = slots; lf.d_model = d; return lf;
   };
-  __nv_bfloat16* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
+  op16_t* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
   {  // zero pad row (t = -1) of every sample
     zero_rows_kernel<<<nc, 128, 0, stream>>>(reinterpret_cast<uint4*>(h1), (size_t)3001 * d * 2 / 16, d * 2 / 16);
     LAUNCH_CHECK();
@@ -901,7 +946,7 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     GWW_TRY(run_gemm(g, stream));
   }
   int slots_in = stat_slots_of(d, bn_d);   // slots written by the GEMM that last produced x
-  __nv_bfloat16* qkv = ws.g;
+  op16_t* qkv = ws.g;
   // when only last_hidden_state[:, -1, :] is consumed, the final layer needs all tokens'
   // K and V but only the last token's query row, out-projection, MLP and final LayerNorm.
   const bool prune = (last_hidden == nullptr && pooled != nullptr && use_last_token && g_prune_last.load() != 0);
@@ -909,13 +954,13 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
     const LayerDev& ld = m->layers[li];
     if (prune && li + 1 == m->layers.size()) {
       const int T = GWW_N_CTX;
-      __nv_bfloat16* hl = ws.h;                          // [nc, d] attention output of the last token
-      __nv_bfloat16* hl2 = ws.h + (size_t)nc * d;        // [nc, d] LN2 output
+      op16_t* hl = ws.h;                          // [nc, d] attention output of the last token
+      op16_t* hl2 = ws.h + (size_t)nc * d;        // [nc, d] LN2 output
       if (fold) {
         GWW_TRY(run_linear(ws.xb, ld.qkv_wf, qkv, ld.qkv_c2, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV,
                            consume(ld.qkv_c1, slots_in)));
       } else {
-        GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
+        GWW_TRY(run_ln_t<op16_t>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
         GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
       }
       {
@@ -927,7 +972,7 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
         LAUNCH_CHECK();
       }
       GWW_TRY(run_linear(hl, ld.o_w, ws.x_last, ld.o_b, ws.x_last, nc, d, d, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_O));
-      GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x_last, hl2, ld.ln2_g, ld.ln2_b, nc, d, 0, 1, stream));
+      GWW_TRY(run_ln_t<op16_t>(ws.x_last, hl2, ld.ln2_g, ld.ln2_b, nc, d, 0, 1, stream));
       GWW_TRY(run_linear(hl2, ld.fc1_w, ws.g, ld.fc1_b, nullptr, nc, f, d, EPI_BIAS_GELU_BF16, bn_f, stream, PK_GEMM_FC1));
       GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x_last, ld.fc2_b, ws.x_last, nc, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2));
       GWW_TRY(run_ln_t<float>(ws.x_last, pooled, m->lnp_g, m->lnp_b, nc, d, 0, 1, stream));
@@ -945,11 +990,11 @@ static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float*
       slots_in = stat_slots_of(d, bn_d);
       continue;
     }
-    GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
+    GWW_TRY(run_ln_t<op16_t>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
     GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
     GWW_TRY(run_attention(qkv, ws.h, nc, GWW_N_CTX, d, stream));
     GWW_TRY(run_linear(ws.h, ld.o_w, ws.x, ld.o_b, ws.x, M, d, d, EPI_BIAS_RESID_F32, bn_o, stream, PK_GEMM_O));
-    GWW_TRY(run_ln_t<__nv_bfloat16>(ws.x, ws.h, ld.ln2_g, ld.ln2_b, M, d, 0, 1, stream));
+    GWW_TRY(run_ln_t<op16_t>(ws.x, ws.h, ld.ln2_g, ld.ln2_b, M, d, 0, 1, stream));
     GWW_TRY(run_linear(ws.h, ld.fc1_w, ws.g, ld.fc1_b, nullptr, M, f, d, EPI_BIAS_GELU_BF16, bn_f, stream, PK_GEMM_FC1));
     GWW_TRY(run_linear(ws.g, ld.fc2_w, ws.x, ld.fc2_b, ws.x, M, d, f, EPI_BIAS_RESID_F32, bn_d, stream, PK_GEMM_FC2));
   }
@@ -990,6 +1035,22 @@ extern "C" int gww_logmel_frontend(const float* strain, long n, float* feats, vo
   if (!strain || !feats || n < 0) return fail(GWW_ERR_INVALID, "logmel_frontend: bad argument");
   if (n == 0) return GWW_OK;
   return run_logmel(strain, n, feats, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int gww_resample_16k(const float* strain, long n, float* audio, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || !audio || n < 0) return fail(GWW_ERR_INVALID, "resample_16k: bad argument");
+  if ((reinterpret_cast<uintptr_t>(audio) & 15) != 0) return fail(GWW_ERR_INVALID, "resample_16k: audio must be 16-byte aligned");
+  if (n == 0) return GWW_OK;
+  return run_logmel(strain, n, nullptr, nullptr, (cudaStream_t)stream, nullptr, audio);
+}
+
+extern "C" int gww_logmel_from_16k(const float* audio, long n, float* feats, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!audio || !feats || n < 0) return fail(GWW_ERR_INVALID, "logmel_from_16k: bad argument");
+  if ((reinterpret_cast<uintptr_t>(audio) & 15) != 0) return fail(GWW_ERR_INVALID, "logmel_from_16k: audio must be 16-byte aligned");
+  if (n == 0) return GWW_OK;
+  return run_logmel(nullptr, n, feats, nullptr, (cudaStream_t)stream, audio, nullptr);
 }
 
 extern "C" int gww_encoder_forward(const gww_model_t* m, const float* feats, long n, float* last_hidden,
@@ -1295,10 +1356,10 @@ static int qf_ensure_device(gww_qfront* qf) {
   GWW_TRY(qf_upload(qf, qf->h_orig, &pl.orig));
   GWW_TRY(qf_upload(qf, qf->h_window, &pl.window));
   GWW_TRY(qf_upload(qf, tw, &pl.tw2048));
-  CU_TRY(cudaFuncSetAttribute(qscan_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQsSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(qscan_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQiMaxRows * 512 * 4));
-  CU_TRY(cudaFuncSetAttribute(qadapter_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes));
-  CU_TRY(cudaFuncSetAttribute(qadapter_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3SmemBytes));
+  GWW_TRY(ensure_smem_attr(qscan_tiles_kernel, kQsSmemBytes));
+  GWW_TRY(ensure_smem_attr(qscan_interp_kernel, kQiMaxRows * 512 * 4));
+  GWW_TRY(ensure_smem_attr(qadapter_conv2_kernel, kC2SmemBytes));
+  GWW_TRY(ensure_smem_attr(qadapter_conv3_kernel, kC3SmemBytes));
   qf->on_device = true;
   return GWW_OK;
 }
@@ -1416,7 +1477,7 @@ static int run_qscan(const gww_qfront* qf, const float* strain, long n, long win
 
 // adapter CNN on spec [n,F,T] -> f32 [n,80,3000] and/or bf16 time-major rows of feats_tm
 static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det, float* feats_f32,
-                        __nv_bfloat16* feats_tm, long tm_stride_w, long tm_off, const QWorkspace& ws,
+                        op16_t* feats_tm, long tm_stride_w, long tm_off, const QWorkspace& ws,
                         cudaStream_t s) {
   if (!qf->has_adapter) return fail(GWW_ERR_INVALID, "qadapter: no adapter weights set");
   if (det < 0 || det >= qf->n_detectors) return fail(GWW_ERR_INVALID, "qadapter: det_idx=%d out of range", det);
@@ -1520,6 +1581,144 @@ extern "C" int gww_stream_search_qscan(const gww_model_t* m, const gww_qfront_t*
   return GWW_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// whitening (MLGWSC-1/inference.py:56-137; kernels in whiten.cuh)
+// ------------------------------------------------------------------------------------------------
+struct WhitenPlan {
+  long n, n_seg, first, nk;
+  int seg_len, log2n, seg_stride, nb, L, H, cs_chunks;
+  // workspace
+  double2* tw; double *seg_psd, *psd0, *inv_asd, *mag, *partial, *q, *qt, *w;
+  size_t total;
+};
+static int whiten_plan(long n, int seg_len, int seg_stride, int max_filter_len, int fir_half, uint8_t* base, WhitenPlan* pl) {
+  if (n < 2 || (n & 1)) return fail(GWW_ERR_INVALID, "whiten: the number of samples must be even (got %ld)", n);
+  int log2n = 0;
+  while ((1 << log2n) < seg_len) ++log2n;
+  if ((1 << log2n) != seg_len || seg_len < 16 || seg_len > kWhMaxSegLen)
+    return fail(GWW_ERR_INVALID, "whiten: Welch segment length %d must be a power of two in [16, %d]", seg_len, kWhMaxSegLen);
+  if (seg_stride < 1 || seg_stride > seg_len) return fail(GWW_ERR_INVALID, "whiten: bad segment stride %d", seg_stride);
+  if (max_filter_len < 2 || (max_filter_len & 1) || max_filter_len > 4096 || max_filter_len > n)
+    return fail(GWW_ERR_INVALID, "whiten: max_filter_len=%d must be even, <= 4096 and <= n", max_filter_len);
+  // pycbc.psd.welch segmentation
+  long n_seg = n / seg_stride;
+  if ((n_seg - 1) * seg_stride + seg_len > n) n_seg -= 1;
+  while (n_seg >= 1 && (n_seg - 1) * seg_stride + seg_len > n) n_seg -= 1;
+  if (n_seg < 1) return fail(GWW_ERR_INVALID, "whiten: %ld samples are too few for one Welch segment of %d", n, seg_len);
+  const long data_len = (n_seg - 1) * seg_stride + seg_len;
+  const long diff = n - data_len;
+  long first = diff / 2;
+  if (diff % 2) first += 1;
+  pl->n = n; pl->n_seg = n_seg; pl->first = first; pl->nk = n / 2 + 1;
+  pl->seg_len = seg_len; pl->log2n = log2n; pl->seg_stride = seg_stride; pl->nb = seg_len / 2 + 1;
+  pl->L = max_filter_len;
+  long H = fir_half > 0 ? fir_half : 8192;
+  if (H < max_filter_len / 2) H = max_filter_len / 2;
+  if (H > n / 2 - 1) H = n / 2 - 1;
+  if (H > 11264) H = 11264;                  // shared-memory tile of the FIR: (2048 + 2H) * 9/8 doubles <= 227 KB
+  pl->H = (int)H;
+  pl->cs_chunks = (int)((pl->nk + kCsChunk - 1) / kCsChunk);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base + o; };
+  pl->tw = (double2*)take((size_t)seg_len / 2 * sizeof(double2));
+  pl->seg_psd = (double*)take((size_t)n_seg * pl->nb * 8);
+  pl->psd0 = (double*)take((size_t)pl->nb * 8);
+  pl->inv_asd = (double*)take((size_t)pl->nk * 8);
+  pl->mag = (double*)take((size_t)pl->nk * 8);
+  const int max_out = (pl->H + 1 > pl->L / 2 + 1) ? pl->H + 1 : pl->L / 2 + 1;
+  pl->partial = (double*)take((size_t)pl->cs_chunks * max_out * 8);
+  pl->q = (double*)take((size_t)(pl->L / 2 + 1) * 8);
+  pl->qt = (double*)take((size_t)pl->L * 8);
+  pl->w = (double*)take((size_t)(pl->H + 1) * 8);
+  pl->total = off;
+  return GWW_OK;
+}
+
+extern "C" size_t gww_whiten_workspace_bytes(long n, int seg_len, int seg_stride, int max_filter_len, int fir_half) {
+  WhitenPlan pl;
+  if (whiten_plan(n, seg_len, seg_stride, max_filter_len, fir_half, nullptr, &pl) != GWW_OK) return 0;
+  return pl.total + 1024;
+}
+
+static double whiten_median_bias(long n) {   // pycbc.psd.estimate.median_bias
+  if (n >= 1000) return std::log(2.0);
+  double ans = 1.0;
+  for (long i = 1; i < (long)((n - 1) / 2 + 1); ++i) ans += 1.0 / (2 * i + 1) - 1.0 / (2 * i);
+  return ans;
+}
+
+extern "C" int gww_whiten(const double* strain, long n, double delta_t, int seg_len, int seg_stride,
+                          int max_filter_len, double low_frequency_cutoff, int trunc_hann, int remove_corrupted,
+                          int fir_half, double* white, float* white_f32, double* psd_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  GWW_TRY(gww_device_ok());
+  if (!strain || (!white && !white_f32) || !(delta_t > 0)) return fail(GWW_ERR_INVALID, "whiten: bad argument");
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  WhitenPlan pl;
+  GWW_TRY(whiten_plan(n, seg_len, seg_stride, max_filter_len, fir_half, base, &pl));
+  if (workspace == nullptr || workspace_bytes < pl.total + (size_t)(base - reinterpret_cast<uint8_t*>(workspace)))
+    return fail(GWW_ERR_WORKSPACE, "whiten: workspace too small (need %zu bytes)", pl.total + 1024);
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(PK_WHITEN, s);
+  // 1. Welch PSD
+  whiten_twiddle_kernel<<<(seg_len / 2 + 255) / 256, 256, 0, s>>>(pl.tw, seg_len);
+  LAUNCH_CHECK();
+  GWW_TRY(ensure_smem_attr(welch_segments_kernel, 2 * kWhMaxSegLen * 16));
+  {
+    const long grid = pl.n_seg < 8L * g_num_sms ? pl.n_seg : 8L * g_num_sms;
+    welch_segments_kernel<<<(unsigned)grid, 256, (size_t)2 * seg_len * 16, s>>>(strain, pl.first, seg_len, pl.log2n, seg_stride,
+                                                                             pl.n_seg, delta_t, pl.tw, pl.seg_psd);
+    LAUNCH_CHECK();
+  }
+  {
+    double sumw2 = 0.0;
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < seg_len; ++i) {
+      const double w = 0.5 - 0.5 * std::cos(2.0 * PI * i / (seg_len - 1));
+      sumw2 += w * w;
+    }
+    const double delta_f = 1.0 / delta_t / seg_len;
+    const double scale = 2.0 * delta_f * seg_len / sumw2;
+    welch_median_kernel<<<pl.nb, 256, 0, s>>>(pl.seg_psd, pl.n_seg, pl.nb, 1.0 / whiten_median_bias(pl.n_seg), scale, pl.psd0);
+    LAUNCH_CHECK();
+    if (psd_out) CU_TRY(cudaMemcpyAsync(psd_out, pl.psd0, (size_t)pl.nb * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  // 2. interpolate + inverse ASD
+  const double psd_df = 1.0 / delta_t / seg_len;
+  const double df = 1.0 / ((double)n * delta_t);
+  long kmin = 1;
+  if (low_frequency_cutoff > 0.0) kmin = (long)(low_frequency_cutoff / df);
+  inv_asd_kernel<<<(unsigned)((pl.nk + 255) / 256), 256, 0, s>>>(pl.psd0, pl.nb, psd_df, df, pl.nk, kmin, pl.inv_asd);
+  LAUNCH_CHECK();
+  // 3. q = irfft(inv_asd) at taps 0..L/2, truncation window
+  const int nq = pl.L / 2 + 1;
+  cosine_series_kernel<<<dim3(pl.cs_chunks, (nq + kCsThreads - 1) / kCsThreads), kCsThreads, 0, s>>>(pl.inv_asd, pl.nk, n, nq, pl.partial);
+  LAUNCH_CHECK();
+  cosine_series_reduce_kernel<<<(nq + 255) / 256, 256, 0, s>>>(pl.partial, pl.cs_chunks, nq, 1.0 / (double)n, pl.q);
+  LAUNCH_CHECK();
+  trunc_window_kernel<<<(pl.L + 255) / 256, 256, 0, s>>>(pl.q, pl.L, trunc_hann, pl.qt);
+  LAUNCH_CHECK();
+  // 4. |Q|
+  GWW_TRY(ensure_smem_attr(filter_mag_kernel, 4096 * 8));
+  filter_mag_kernel<<<(unsigned)((pl.nk + 255) / 256), 256, (size_t)pl.L * 8, s>>>(pl.qt, pl.L, pl.nk, n, pl.mag);
+  LAUNCH_CHECK();
+  // 5. w = irfft(|Q|) at taps 0..H, circular FIR, crop
+  const int nw = pl.H + 1;
+  cosine_series_kernel<<<dim3(pl.cs_chunks, (nw + kCsThreads - 1) / kCsThreads), kCsThreads, 0, s>>>(pl.mag, pl.nk, n, nw, pl.partial);
+  LAUNCH_CHECK();
+  cosine_series_reduce_kernel<<<(nw + 255) / 256, 256, 0, s>>>(pl.partial, pl.cs_chunks, nw, 1.0 / (double)n, pl.w);
+  LAUNCH_CHECK();
+  const long n0 = remove_corrupted ? pl.L / 2 : 0;
+  const long n_out = remove_corrupted ? n - pl.L : n;
+  if (n_out <= 0) return fail(GWW_ERR_INVALID, "whiten: nothing left after removing the corrupted edges");
+  const size_t fir_smem = (size_t)(kFirTile + 2 * pl.H + (kFirTile + 2 * pl.H) / 8 + 8) * 8;
+  GWW_TRY(ensure_smem_attr(fir_apply_kernel, (int)fir_smem));
+  fir_apply_kernel<<<(unsigned)((n_out + kFirTile - 1) / kFirTile), kFirThreads, fir_smem, s>>>(strain, n, pl.w, pl.H, n0, n_out,
+                                                                                             white, white_f32);
+  LAUNCH_CHECK();
+  return GWW_OK;
+}
+
 // ---- building blocks -------------------------------------------------------------------------------
 extern "C" int gww_gemm_bf16(const void* A, const void* W, void* C, const float* bias, const float* resid,
                              const float* pos, long M, int N, int K, int epilogue, int block_n,
@@ -1553,6 +1752,6 @@ extern "C" int gww_layernorm(const float* x, void* out, const float* gamma, cons
                              int d, int out_bf16, void* stream) {
   GWW_TRY(gww_device_ok());
   if (!x || !out || rows <= 0) return fail(GWW_ERR_INVALID, "layernorm: bad argument");
-  if (out_bf16) return run_ln_t<__nv_bfloat16>(x, (__nv_bfloat16*)out, gamma, beta, rows, d, 0, 1, (cudaStream_t)stream);
+  if (out_bf16) return run_ln_t<op16_t>(x, (op16_t*)out, gamma, beta, rows, d, 0, 1, (cudaStream_t)stream);
   return run_ln_t<float>(x, (float*)out, gamma, beta, rows, d, 0, 1, (cudaStream_t)stream);
 }

@@ -59,7 +59,13 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 
 __global__ void __launch_bounds__(kLmThreads, 1)
 logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict__ out_f32,
-              __nv_bfloat16* __restrict__ out_tm, const LogmelTables tb) {
+              op16_t* __restrict__ out_tm, const LogmelTables tb,
+              const float* __restrict__ audio_in, float* __restrict__ audio_out) {
+  // audio_in  != nullptr: the input is already 16 kHz audio [n,16000] f32 (what the reference's datasets
+  //                       store, preprocess.py:94-98, and hand to WhisperFeatureExtractor, dataset.py:20-24):
+  //                       phases 1-2 are skipped.
+  // audio_out != nullptr: the resampled audio is written out [n,16000] f32 (resample_timeseries alone when
+  //                       both feature outputs are null).
   extern __shared__ __align__(16) uint8_t lm_smem[];
   float* y = reinterpret_cast<float*>(lm_smem);
   double2* Cm = reinterpret_cast<double2*>(lm_smem + kLmSmemY);
@@ -75,6 +81,10 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
 
   for (long w = blockIdx.x; w < n_detwin; w += gridDim.x) {
     __syncthreads();
+    if (audio_in != nullptr) {
+      const float4* a4 = reinterpret_cast<const float4*>(audio_in + w * 16000L);
+      for (int i = tid; i < 4000; i += kLmThreads) reinterpret_cast<float4*>(y)[i] = a4[i];
+    } else {
     // ---------------- phase 1: FFT-2048 (Stockham radix-2 DIF, ping-pong in scratch)
     double2* fa = reinterpret_cast<double2*>(scratch);
     double2* fb = fa + 2048;
@@ -161,7 +171,13 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
         __syncwarp();
       }
     }
+    }  // audio_in == nullptr
     __syncthreads();
+    if (audio_out != nullptr) {
+      float4* a4 = reinterpret_cast<float4*>(audio_out + w * 16000L);
+      for (int i = tid; i < 4000; i += kLmThreads) a4[i] = reinterpret_cast<const float4*>(y)[i];
+      if (out_f32 == nullptr && out_tm == nullptr) continue;
+    }
     // ---------------- phase 3: live frames, kLmFramesPerWarp frames per warp pass.  The folded DFT is a
     // [frames x 199] x [199 x 201] product against the cos/sin table: every twiddle fetched from smem
     // (the binding resource: one 16-byte load per lane per 2 DFMA in the one-frame version, r1 profile)
@@ -285,7 +301,7 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
     }
     if (out_tm != nullptr) {
       uint4* o4 = reinterpret_cast<uint4*>(out_tm + w * (3002L * 80L));
-      const uint32_t cc = pack_bf16x2(cconst, cconst);
+      const uint32_t cc = pack_op16x2(cconst, cconst);
       for (int idx = tid; idx < 3002 * 10; idx += kLmThreads) {
         const int pr = idx / 10, c = idx - pr * 10;
         uint4 v = make_uint4(cc, cc, cc, cc);
@@ -298,7 +314,7 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
           for (int e = 0; e < 4; ++e) {
             const float a0 = (fmaxf(src[2 * e], floorv) + 4.0f) * 0.25f;
             const float a1 = (fmaxf(src[2 * e + 1], floorv) + 4.0f) * 0.25f;
-            pk[e] = pack_bf16x2(a0, a1);
+            pk[e] = pack_op16x2(a0, a1);
           }
           v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
@@ -311,7 +327,7 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
 // Reference-layout features [n,80,3000] f32 (what HF WhisperEncoder.forward takes,
 // modeling_whisper.py:593-617) -> bf16 time-major zero-padded [n,3002,80] for the conv-stem GEMM.
 __global__ void __launch_bounds__(256)
-feats_to_timemajor_kernel(const float* __restrict__ feats, __nv_bfloat16* __restrict__ out_tm) {
+feats_to_timemajor_kernel(const float* __restrict__ feats, op16_t* __restrict__ out_tm) {
   __shared__ float tile[80][65];
   const long w = blockIdx.y;
   const int t0 = blockIdx.x * 64;              // 47 blocks cover 3000 frames (+ pad rows)
@@ -321,12 +337,12 @@ feats_to_timemajor_kernel(const float* __restrict__ feats, __nv_bfloat16* __rest
     tile[mm][tt] = (t0 + tt < 3000) ? src[mm * 3000L + t0 + tt] : 0.f;
   }
   __syncthreads();
-  __nv_bfloat16* dst = out_tm + w * (3002L * 80L);
+  op16_t* dst = out_tm + w * (3002L * 80L);
   for (int i = threadIdx.x; i < 64 * 40; i += 256) {
     const int tt = i / 40, c2 = i - tt * 40;
     if (t0 + tt < 3000) {
       reinterpret_cast<uint32_t*>(dst + (t0 + tt + 1) * 80L)[c2] =
-          pack_bf16x2(tile[2 * c2][tt], tile[2 * c2 + 1][tt]);
+          pack_op16x2(tile[2 * c2][tt], tile[2 * c2 + 1][tt]);
     }
   }
   if (blockIdx.x == 0) {

@@ -678,7 +678,7 @@ qadapter_conv3_kernel(const float* __restrict__ act2, float* __restrict__ map, i
 // grid (ceil(OT/128), n), 256 threads
 __global__ void __launch_bounds__(256)
 qadapter_pool_kernel(const float* __restrict__ map, float* __restrict__ out_f32,
-                     __nv_bfloat16* __restrict__ out_tm, long tm_stride_w, long tm_off, int H, int W,
+                     op16_t* __restrict__ out_tm, long tm_stride_w, long tm_off, int H, int W,
                      int OF, int OT, int det, const QAdapterDev ad) {
   // per-CTA tables: the bin ranges (same float expressions as before, evaluated once per row / column instead of
   // once per output) and the <= 8 source columns this CTA's 128 output columns touch, staged in shared memory
@@ -694,7 +694,7 @@ qadapter_pool_kernel(const float* __restrict__ map, float* __restrict__ out_f32,
   const float* src = map + n * static_cast<long>(H) * W;
   const float g = ad.gamma[det], be = ad.beta[det];
   float* out32 = out_f32 ? out_f32 + n * static_cast<long>(OF) * OT : nullptr;
-  __nv_bfloat16* outtm = out_tm ? out_tm + (n * tm_stride_w + tm_off) * static_cast<long>(OT + 2) * OF : nullptr;
+  op16_t* outtm = out_tm ? out_tm + (n * tm_stride_w + tm_off) * static_cast<long>(OT + 2) * OF : nullptr;
   const bool staged = (OF <= 128 && H <= 128 && nc <= 9);
   if (staged) {
     for (int f = threadIdx.x; f < OF; f += 256)
@@ -732,12 +732,12 @@ qadapter_pool_kernel(const float* __restrict__ map, float* __restrict__ out_f32,
     v = ad.scale * v + ad.bias;
     v = v * g + be;
     if (out32) out32[static_cast<long>(f) * OT + t] = v;
-    if (outtm) outtm[static_cast<long>(t + 1) * OF + f] = __float2bfloat16(v);
+    if (outtm) outtm[static_cast<long>(t + 1) * OF + f] = float_to_op16(v);
   }
   if (outtm && blockIdx.x == 0) {
     for (int i = threadIdx.x; i < OF; i += 256) {
-      outtm[i] = __float2bfloat16(0.f);
-      outtm[static_cast<long>(OT + 1) * OF + i] = __float2bfloat16(0.f);
+      outtm[i] = float_to_op16(0.f);
+      outtm[static_cast<long>(OT + 1) * OF + i] = float_to_op16(0.f);
     }
   }
 }

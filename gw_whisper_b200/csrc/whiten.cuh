@@ -1,0 +1,315 @@
+// Whitening of one strain channel on the GPU: what the reference's
+// `whiten` (MLGWSC-1/inference.py:56-137, psd=None branch) computes through pycbc 2.4.0, restated in
+// oracle/whiten.py and re-designed here for the GPU.  All arithmetic is f64 (pycbc computes in f64 and B200 has a
+// full-rate-class FP64 pipe); parity is UNPINNED upstream (pycbc absent), the oracle restatement is the spec.
+//
+//   1. Welch PSD (pycbc.psd.welch, window='hann', avg_method='median'): segments of seg_len samples every
+//      seg_len/2, numpy.hanning window, |FFT|^2 dt^2 with DC / Nyquist halved            welch_segments_kernel
+//      per-bin median over the segments by an 8x8-bit radix select, / median_bias,
+//      * 2 delta_f seg_len / sum(w^2)                                                    welch_median_kernel
+//   2. pycbc.psd.interpolate onto the N/2+1 bins of the full series; inv_asd = psd^-1/2
+//      between the low-frequency cut-off and Nyquist                                      inv_asd_kernel
+//   3. inverse_spectrum_truncation: q = irfft(inv_asd) is needed at 2 (L/2)+... taps only: a cosine series
+//      evaluated directly, exact phases re-seeded every kCsChunk terms                    cosine_series_kernel
+//      Hann truncation window -> q_t (L taps)                                             trunc_window_kernel
+//   4. |Q_k| = |sum_t q_t e^{-2 pi i t k / N}| on the N/2+1 bins (this IS psd_out^-1/2)    filter_mag_kernel
+//   5. pycbc multiplies rfft(x) by |Q| and transforms back with N-point FFTs (N = the whole segment, hours of
+//      data, any even length).  |Q| is smooth, so w = irfft(|Q|) decays fast (1.4e-7 of its peak beyond L/2,
+//      data, any even length).  |Q| is smooth except for kinks where the truncated filter changes sign below the
+//      cut-off, so w = irfft(|Q|) decays like 1/m^2 (3e-6 of its peak beyond L/2, 4e-9 beyond 8192 taps): the
+//      product is applied as a circular FIR with w truncated to +-H taps.  H = 8192: max deviation from the
+//      N-point-FFT result 4e-5 of the output's rms on detector-like noise, all of it below the cut-off
+//      frequency (measured in tests/test_whiten.py; above 30 Hz the two agree to 1e-7)
+//                                                            cosine_series_kernel + fir_apply_kernel
+//   6. crop L/2 samples at both ends (remove_corrupted).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gww {
+
+constexpr int kWhMaxSegLen = 4096;       // Welch segment length (power of two) supported
+constexpr int kCsChunk = 4096;           // cosine-series terms per exact re-seed of the rotation
+constexpr int kCsThreads = 256;
+constexpr int kFirTile = 2048;           // outputs per CTA of the FIR
+constexpr int kFirThreads = 256;
+constexpr int kFirPerThread = kFirTile / kFirThreads;   // 8 consecutive outputs per thread
+
+__global__ void whiten_twiddle_kernel(double2* __restrict__ tw, int n) {   // tw[j] = e^{-2 pi i j / n}, j < n/2
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n / 2) return;
+  double s, c;
+  sincospi(2.0 * (double)j / (double)n, &s, &c);
+  tw[j] = make_double2(c, -s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1a. Welch segment spectra: one CTA per segment, complex Stockham radix-2 FFT in shared memory.
+//     out[s][k], k = 0..seg_len/2 (f64).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+welch_segments_kernel(const double* __restrict__ x, long first_sample, int seg_len, int log2n, int seg_stride,
+                      long n_segments, double delta_t, const double2* __restrict__ tw /* [seg_len/2] e^{-2 pi i j/n} */,
+                      double* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t wh_smem[];
+  double2* fa = reinterpret_cast<double2*>(wh_smem);
+  double2* fb = fa + seg_len;
+  const int tid = threadIdx.x;
+  for (long s = blockIdx.x; s < n_segments; s += gridDim.x) {
+    const double* src = x + first_sample + s * seg_stride;
+    for (int i = tid; i < seg_len; i += blockDim.x) {
+      const double w = 0.5 - 0.5 * cospi(2.0 * (double)i / (double)(seg_len - 1));   // numpy.hanning
+      fa[i] = make_double2(src[i] * w, 0.0);
+    }
+    __syncthreads();
+    double2* pa = fa;
+    double2* pb = fb;
+    int n = seg_len, st = 1;
+    for (int stage = 0; stage < log2n; ++stage) {
+      const int m = n >> 1;
+      for (int t = tid; t < seg_len / 2; t += blockDim.x) {
+        const int p = t / st, q = t - p * st;
+        const double2 wp = tw[p * st];
+        const double2 u = pa[q + st * p], v = pa[q + st * (p + m)];
+        pb[q + st * (2 * p)] = make_double2(u.x + v.x, u.y + v.y);
+        const double dx = u.x - v.x, dy = u.y - v.y;
+        pb[q + st * (2 * p + 1)] = make_double2(dx * wp.x - dy * wp.y, dx * wp.y + dy * wp.x);
+      }
+      __syncthreads();
+      double2* t2 = pa; pa = pb; pb = t2;
+      n >>= 1; st <<= 1;
+    }
+    const int half = seg_len / 2;
+    double* dst = out + s * (long)(half + 1);
+    for (int k = tid; k <= half; k += blockDim.x) {
+      const double re = pa[k].x * delta_t, im = pa[k].y * delta_t;
+      double p = re * re + im * im;
+      if (k == 0 || k == half) p *= 0.5;
+      dst[k] = p;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1b. per-bin median over the segments: radix select on the f64 bit patterns (all values >= 0, so the
+//     unsigned order of the bits is the numeric order).  One CTA per frequency bin.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long wh_select(const double* __restrict__ col, long stride, long n, long rank,
+                                                        unsigned int* hist /* smem [256] */) {
+  unsigned long long prefix = 0ull, mask = 0ull;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long v = (unsigned long long)__double_as_longlong(col[i * stride]);
+      if ((v & mask) == prefix) atomicAdd(&hist[(unsigned)((v >> shift) & 0xffull)], 1u);
+    }
+    __syncthreads();
+    // every thread walks the 256 counters (uniform result, no extra barrier state)
+    long r = rank;
+    unsigned digit = 0;
+    for (unsigned d = 0; d < 256; ++d) {
+      const unsigned c = hist[d];
+      if (r < (long)c) { digit = d; break; }
+      r -= c;
+    }
+    rank = r;
+    prefix |= (unsigned long long)digit << shift;
+    mask |= 0xffull << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(256)
+welch_median_kernel(const double* __restrict__ seg_psd, long n_segments, int n_bins, double inv_bias, double scale,
+                    double* __restrict__ psd) {
+  __shared__ unsigned int hist[256];
+  const int k = blockIdx.x;
+  if (k >= n_bins) return;
+  const double* col = seg_psd + k;
+  const long lo = (n_segments - 1) / 2, hi = n_segments / 2;
+  const double a = __longlong_as_double((long long)wh_select(col, n_bins, n_segments, lo, hist));
+  double med = a;
+  if (hi != lo) {
+    const double b = __longlong_as_double((long long)wh_select(col, n_bins, n_segments, hi, hist));
+    med = (a + b) / 2.0;                                     // numpy.median: mean of the two middle values
+  }
+  if (threadIdx.x == 0) psd[k] = med * inv_bias * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. interpolate the Welch PSD to the full resolution and take psd^-1/2 inside [kmin, N/2)
+// ------------------------------------------------------------------------------------------------
+__global__ void inv_asd_kernel(const double* __restrict__ psd0, int n_bins0, double psd_df, double df, long nk /* N/2+1 */,
+                               long kmin, double* __restrict__ inv_asd) {
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nk) return;
+  double v = 0.0;
+  if (k >= kmin && k < nk - 1) {
+    const double f = (double)k * df;                         // numpy.arange(n) * delta_f
+    long j = (long)floor(f / psd_df);
+    if (j > n_bins0 - 2) j = n_bins0 - 2;
+    if (j < 0) j = 0;
+    const double x0 = (double)j * psd_df, x1 = (double)(j + 1) * psd_df;
+    const double y0 = psd0[j], y1 = psd0[j + 1];
+    const double p = (f >= x1) ? y1 : ((y1 - y0) / (x1 - x0) * (f - x0) + y0);   // numpy.interp
+    v = sqrt(1.0 / p);                                       // (1.0 / psd) ** 0.5
+  }
+  inv_asd[k] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3/5. cosine series: y[m] = (1/N) [ a_0 + 2 sum_{k=1}^{N/2-1} a_k cos(2 pi m k / N) + a_{N/2} (-1)^m ],
+//      m = 0..n_out-1  == numpy.fft.irfft(a, N)[m] for a real half spectrum a.
+//      grid (k-chunks, ceil(n_out / 256)); thread = one m; per chunk the phase is seeded exactly
+//      ((m k0) mod N in integers) and advanced by complex rotation.  Partial sums per chunk are written out and
+//      reduced in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCsThreads)
+cosine_series_kernel(const double* __restrict__ a, long nk, long N, int n_out, double* __restrict__ partial /* [chunks][n_out] */) {
+  __shared__ double a_s[kCsChunk];
+  const long k0 = (long)blockIdx.x * kCsChunk;
+  const int nchunk = (int)((nk - k0 < kCsChunk) ? (nk - k0) : kCsChunk);
+  for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
+    const long k = k0 + i;
+    const double wgt = (k == 0 || k == nk - 1) ? 1.0 : 2.0;
+    a_s[i] = a[k] * wgt;
+  }
+  __syncthreads();
+  const int m = blockIdx.y * blockDim.x + threadIdx.x;
+  if (m >= n_out) return;
+  const unsigned long long ph = ((unsigned long long)m * (unsigned long long)k0) % (unsigned long long)N;
+  double c, s, dc, ds;
+  sincospi(2.0 * (double)ph / (double)N, &s, &c);
+  sincospi(2.0 * (double)m / (double)N, &ds, &dc);
+  double acc = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < nchunk; ++i) {
+    acc = fma(a_s[i], c, acc);
+    const double c2 = c * dc - s * ds;
+    s = fma(s, dc, c * ds);
+    c = c2;
+  }
+  partial[(long)blockIdx.x * n_out + m] = acc;
+}
+
+__global__ void cosine_series_reduce_kernel(const double* __restrict__ partial, int n_chunks, int n_out, double inv_n,
+                                            double* __restrict__ y) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_out) return;
+  double acc = 0.0;
+  for (int c = 0; c < n_chunks; ++c) acc += partial[(long)c * n_out + m];
+  y[m] = acc * inv_n;
+}
+
+// Hann truncation of q (inverse_spectrum_truncation): q is even, q[0..L/2] given.
+//   qt[t + L/2], t = -L/2 .. L/2-1:  t >= 0: q[t] * hanning(L)[L/2 + t];  t < 0: q[-t] * hanning(L)[L/2 + t]
+// (pycbc: q[0:L/2] *= w[-L/2:], q[N-L/2:N] *= w[0:L/2]); without the window: plain truncation.
+__global__ void trunc_window_kernel(const double* __restrict__ q, int L, int hann, double* __restrict__ qt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const int t = i - L / 2;
+  const double w = hann ? (0.5 - 0.5 * cospi(2.0 * (double)i / (double)(L - 1))) : 1.0;
+  qt[i] = q[t >= 0 ? t : -t] * w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. |Q_k| for k = 0..N/2:  Q_k = sum_{t=-L/2}^{L/2-1} qt[t] e^{-2 pi i t k / N}; one thread per k.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+filter_mag_kernel(const double* __restrict__ qt, int L, long nk, long N, double* __restrict__ mag) {
+  extern __shared__ __align__(16) uint8_t wh_smem[];
+  double* q_s = reinterpret_cast<double*>(wh_smem);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) q_s[i] = qt[i];
+  __syncthreads();
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nk) return;
+  // t = -L/2: phase +2 pi (L/2) k / N
+  const unsigned long long ph = ((unsigned long long)(L / 2) * (unsigned long long)k) % (unsigned long long)N;
+  double c, s, dc, ds;
+  sincospi(2.0 * (double)ph / (double)N, &s, &c);
+  sincospi(2.0 * (double)k / (double)N, &ds, &dc);           // each tap rotates by e^{-i theta}
+  double re = 0.0, im = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < L; ++i) {
+    const double v = q_s[i];
+    re = fma(v, c, re);
+    im = fma(v, s, im);
+    const double c2 = fma(c, dc, s * ds);
+    s = fma(s, dc, -(c * ds));
+    c = c2;
+  }
+  mag[k] = sqrt(re * re + im * im);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. circular FIR: y[n] = sum_{m=-H}^{H} w[|m|] x[(n - m) mod N] for n in [n0, n0 + n_out); CTA = kFirTile
+//    outputs, thread = 8 consecutive outputs with a sliding register window; the staged x tile is stored
+//    with one pad word per 8 so that the 8-strided per-thread addresses spread over the banks.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fir_pad(int p) { return p + (p >> 3); }
+
+__global__ void __launch_bounds__(kFirThreads)
+fir_apply_kernel(const double* __restrict__ x, long N, const double* __restrict__ w /* [H+1] */, int H, long n0, long n_out,
+                 double* __restrict__ y64, float* __restrict__ y32) {
+  extern __shared__ __align__(16) uint8_t wh_smem[];
+  double* x_s = reinterpret_cast<double*>(wh_smem);                 // padded [kFirTile + 2H]
+  const long base = n0 + (long)blockIdx.x * kFirTile;               // first output of the tile
+  const int span = kFirTile + 2 * H;                                // x[base - H .. base + kFirTile - 1 + H]
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    long g = (base - H + i) % N;
+    if (g < 0) g += N;
+    x_s[fir_pad(i)] = x[g];
+  }
+  __syncthreads();
+  // thread handles outputs o = 8 tid + j;  y[base+o] = sum_i w[|i-H|] x_s[(o + 2H) - i]   (tap index i = m + H; the
+  // tile index of x[n-m] is (o - m) + H).  The tap value is a warp-uniform read-only load (L1 broadcast).
+  const int o0 = kFirPerThread * threadIdx.x;
+  double acc[kFirPerThread];
+  double xr[kFirPerThread];
+#pragma unroll
+  for (int j = 0; j < kFirPerThread; ++j) { acc[j] = 0.0; xr[j] = x_s[fir_pad(o0 + j + 2 * H)]; }
+  // invariant: xr[j] = x_s[o0 + j + 2H - i] for the current tap i
+  const int taps = 2 * H + 1;
+  int i = 0;
+  for (; i + kFirPerThread <= taps; i += kFirPerThread) {
+    double wv[kFirPerThread];
+#pragma unroll
+    for (int u = 0; u < kFirPerThread; ++u) {
+      const int d = i + u - H;
+      wv[u] = __ldg(w + (d < 0 ? -d : d));
+    }
+#pragma unroll
+    for (int u = 0; u < kFirPerThread; ++u) {
+#pragma unroll
+      for (int j = 0; j < kFirPerThread; ++j) acc[j] = fma(wv[u], xr[j], acc[j]);
+      // slide: xr[j] <- xr[j-1], xr[0] <- x_s[o0 + 2H - (i+u+1)]
+#pragma unroll
+      for (int j = kFirPerThread - 1; j > 0; --j) xr[j] = xr[j - 1];
+      const int idx = o0 + 2 * H - (i + u + 1);
+      xr[0] = (idx >= 0) ? x_s[fir_pad(idx)] : 0.0;
+    }
+  }
+  for (; i < taps; ++i) {
+    const int d = i - H;
+    const double wv = __ldg(w + (d < 0 ? -d : d));
+#pragma unroll
+    for (int j = 0; j < kFirPerThread; ++j) acc[j] = fma(wv, xr[j], acc[j]);
+#pragma unroll
+    for (int j = kFirPerThread - 1; j > 0; --j) xr[j] = xr[j - 1];
+    const int idx = o0 + 2 * H - (i + 1);
+    xr[0] = (idx >= 0) ? x_s[fir_pad(idx)] : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < kFirPerThread; ++j) {
+    const long o = (long)blockIdx.x * kFirTile + o0 + j;
+    if (o < n_out) {
+      if (y64) y64[o] = acc[j];
+      if (y32) y32[o] = (float)acc[j];
+    }
+  }
+}
+
+}  // namespace gww

@@ -228,6 +228,8 @@ class GWWhisperClassifier(nn.Module):
                       batch: int = 256):
         """Sliding-window search used by `inference.evaluate_slices`: batches of 256 consecutive windows
         (the reference's DataLoader batch, inference.py:465), score = out[:, 0] (:481)."""
+        if not strain.is_cuda:
+            raise RuntimeError("gw_whisper_b200 has no CPU path: stream_search needs the segment on the GPU")
         self._sync_head()
         enc, qt = self.encoder, self.adapter.q_transform
         D, N = strain.shape

@@ -103,11 +103,11 @@ def gather_triggers(seg: torch.Tensor, idx: torch.Tensor, score: torch.Tensor,
 
 
 def gather_scores(pieces: Sequence[ShardPiece], scores: Sequence[torch.Tensor],
-                  windows_per_segment: Sequence[int], group: Optional[dist.ProcessGroup] = None
-                  ) -> List[torch.Tensor]:
+                  windows_per_segment: Sequence[int], group: Optional[dist.ProcessGroup] = None,
+                  device: Optional[torch.device] = None) -> List[torch.Tensor]:
     """Reassemble the per-window scores (`all_vals` of the reference) of every segment on every
     rank: each rank contributes its pieces; result[s] is a [windows_per_segment[s]] f32 tensor."""
-    dev = scores[0].device if len(scores) else torch.device("cpu")
+    dev = device if device is not None else (scores[0].device if len(scores) else torch.device("cpu"))
     total = int(sum(windows_per_segment))
     offs = [0]
     for nw in windows_per_segment:
@@ -123,22 +123,28 @@ def gather_scores(pieces: Sequence[ShardPiece], scores: Sequence[torch.Tensor],
 
 def sharded_search(network, segments: Sequence[torch.Tensor], hop: int, threshold: float,
                    rank: int = 0, world: int = 1, group: Optional[dist.ProcessGroup] = None,
-                   batch: int = BATCH):
-    """Search `segments` (list of [D, n_samples] strain tensors, resident on this rank's device or
-    host) with `network.stream_search(strain, hop, n_windows, thr, first_window)`; every rank
-    processes its pieces and all ranks return the same (seg, window, score) trigger list and the
-    per-segment score arrays."""
+                   batch: int = BATCH, device: Optional[torch.device] = None):
+    """Search `segments` (list of [D, n_samples] strain tensors; host or device resident) with
+    `network.stream_search(strain, hop, n_windows, thr, first_window)`.  Every rank processes its own pieces --
+    it touches (and, for host-resident segments, uploads) only the sample range of each piece plus the
+    (2048 - hop)-sample halo, `ShardPiece.sample_range` -- and all ranks return the same (seg, window, score)
+    trigger list and the per-segment score arrays.  Window indices are global (segment-relative)."""
     nws = [n_windows(int(s.shape[-1]), hop) for s in segments]
     plan = plan_shards(nws, world, batch)
     mine = plan[rank]
     t_seg, t_idx, t_sc, sc_list = [], [], [], []
-    dev = None
+    dev = device
     for p in mine:
-        strain = segments[p.segment]
-        scores, idx, sc = network.stream_search(strain, hop, p.n_windows, threshold, first_window=p.first_window)
+        lo, hi = p.sample_range(hop)
+        strain = segments[p.segment][:, lo:hi]
+        if device is not None and strain.device != torch.device(device):
+            strain = strain.to(device, non_blocking=True)
+        strain = strain.contiguous()
+        # the slice starts at the piece's first window: local window k == global window first_window + k
+        scores, idx, sc = network.stream_search(strain, hop, p.n_windows, threshold, first_window=0)
         dev = scores.device
         sc_list.append(scores)
-        t_idx.append(idx.to(torch.int64))
+        t_idx.append(idx.to(torch.int64) + p.first_window)
         t_sc.append(sc.to(torch.float32))
         t_seg.append(torch.full_like(idx, p.segment, dtype=torch.int64))
     if dev is None:
@@ -147,5 +153,5 @@ def sharded_search(network, segments: Sequence[torch.Tensor], hop: int, threshol
     seg, idx, sc = gather_triggers(cat(t_seg, torch.int64), cat(t_idx, torch.int64), cat(t_sc, torch.float32), group)
     if not sc_list:
         sc_list, mine = [torch.empty(0, device=dev)], []
-    all_scores = gather_scores(mine, sc_list, nws, group) if nws else []
+    all_scores = gather_scores(mine, sc_list, nws, group, device=dev) if nws else []
     return (seg, idx, sc), all_scores

@@ -16,6 +16,32 @@ SIZES = {
 }
 
 
+# Multipliers (q/k projections, other layer matrices, conv stem) of the "spread" weight set per size
+# (default init gives logits with a 1e-4 spread across windows, which makes parity vacuous).
+# tiny/base: probed in round 1 -- lifts the std of the last-token representation across Gaussian-noise
+# windows from 1.2e-4 to ~4e-2 while PyTorch's own bf16 autocast of the same model still agrees with fp32 to
+# ~1e-2 (x20 on q,k gives a 0.4 spread but is chaotic: torch bf16 autocast itself is then off by O(1)).
+# base / small (round 2, tools/condition_search.py on a B200, 48 windows, profiles/r2_condition_search.txt): with
+# (6, 3, 3) the twelve layers of whisper-small are a chaotic map (torch's own bf16 autocast is off by ~1.0 on the
+# logits, fp16 autocast by 8e-2); the sets below keep the logit spread across windows >= 0.12 while fp16-operand
+# arithmetic stays within 1e-2 of fp32 (spread / max error ~ 17-18; bf16 operands: ~2).
+CONDITIONED = {"tiny": (6.0, 3.0, 3.0), "base": (6.0, 1.0, 3.0), "small": (4.0, 1.0, 3.0)}
+
+
+def scale_encoder_(enc: nn.Module, qk: float, layer: float, conv: float) -> nn.Module:
+    """In-place rescale of a random-init HF WhisperEncoder: q/k projection weights by `qk`, every other 2-D
+    layer matrix by `layer`, the conv-stem weights by `conv`."""
+    with torch.no_grad():
+        for name, p in enc.named_parameters():
+            if name.endswith("q_proj.weight") or name.endswith("k_proj.weight"):
+                p.mul_(qk)
+            elif name.startswith("layers.") and name.endswith("weight") and p.dim() == 2:
+                p.mul_(layer)
+            elif name.startswith("conv") and name.endswith("weight"):
+                p.mul_(conv)
+    return enc
+
+
 def make_encoder(size: str = "tiny", seed: int = 0, init_std: Optional[float] = None,
                  spread: bool = False) -> nn.Module:
     """Random-init HF WhisperEncoder (fp32, eval).  `spread=True` rescales the projection / MLP
@@ -33,18 +59,7 @@ def make_encoder(size: str = "tiny", seed: int = 0, init_std: Optional[float] = 
     torch.manual_seed(seed)
     enc = WhisperEncoder(cfg).float().eval()
     if spread:
-        # probed in this container: (q,k x6; other layer matrices x3; conv x3) lifts the std of the
-        # last-token representation across Gaussian-noise windows from 1.2e-4 to ~4e-2 while PyTorch's
-        # own bf16 autocast of the same model still agrees with fp32 to ~1e-2 (x20 on q,k gives a 0.4
-        # spread but is chaotic: torch bf16 autocast itself is then off by O(1))
-        with torch.no_grad():
-            for name, p in enc.named_parameters():
-                if name.endswith("q_proj.weight") or name.endswith("k_proj.weight"):
-                    p.mul_(6.0)
-                elif name.startswith("layers.") and name.endswith("weight") and p.dim() == 2:
-                    p.mul_(3.0)
-                elif name.startswith("conv") and name.endswith("weight"):
-                    p.mul_(3.0)
+        scale_encoder_(enc, *CONDITIONED[size])
     return enc
 
 

@@ -93,11 +93,16 @@ typedef struct {
 /* ---- library / device ------------------------------------------------------------------------ */
 const char* gww_last_error(void);
 const char* gww_version(void);
+/* "f16" or "bf16": the 16-bit tensor-core operand type this library was built with (activations and weights fed
+ * to tcgen05.mma; accumulation is fp32 either way).  libgww_b200.so is the fp16 build (Whisper is an fp16
+ * model; 8x less operand rounding than bf16 against the fp32 reference), libgww_b200_bf16.so the bf16 one.
+ * The building-block entry points below that take "16-bit" device buffers use this type. */
+const char* gww_operand_dtype(void);
 /* 0 if the current device is sm_100 and the kernels can run, else GWW_ERR_NO_DEVICE. */
 int gww_device_ok(void);
 
 /* ---- model handle ---------------------------------------------------------------------------- */
-/* Uploads weights, merges DoRA, casts matrices to bf16 (fp32 merge), folds the
+/* Uploads weights, merges DoRA, casts matrices to the 16-bit operand type (fp32 merge), folds the
  * head_dim^-0.5 query scale into W_q/b_q.  Immutable afterwards; one in-flight call per workspace. */
 int gww_model_create(const gww_encoder_config_t* cfg, const gww_encoder_weights_t* w,
                      gww_model_t** out);
@@ -109,6 +114,16 @@ size_t gww_workspace_bytes(const gww_model_t* m, int chunk);
 /* ---- front end A (replaces scipy.signal.resample + WhisperFeatureExtractor) -------------------- */
 /* strain: device f32 [n, 2048]; feats: device f32 [n, 80, 3000] (reference layout/dtype). */
 int gww_logmel_frontend(const float* strain, long n, float* feats, void* stream);
+
+/* The two halves of front end A on their own, for callers that keep the reference's on-disk format (the
+ * reference stores the RESAMPLED 16 kHz audio, Signal_vs_Noise/utils/preprocess.py:44-51,94-98, and feeds it to
+ * WhisperFeatureExtractor per item, Signal_vs_Noise/src/dataset.py:20-24):
+ *   gww_resample_16k     == scipy.signal.resample(x, 16000) stored as f32: strain device f32 [n, 2048] ->
+ *                           audio device f32 [n, 16000] (16-byte aligned)
+ *   gww_logmel_from_16k  == WhisperFeatureExtractor(audio, sampling_rate=16000).input_features:
+ *                           audio device f32 [n, 16000] -> feats device f32 [n, 80, 3000] */
+int gww_resample_16k(const float* strain, long n, float* audio, void* stream);
+int gww_logmel_from_16k(const float* audio, long n, float* feats, void* stream);
 
 /* ---- encoder (replaces HF WhisperEncoder.forward with merged DoRA) ----------------------------- */
 /* feats: device f32 [n, 80, 3000].  Exactly one of the outputs may be NULL:
@@ -199,14 +214,29 @@ int gww_stream_search_qscan(const gww_model_t* m, const gww_qfront_t* qf, const 
                             int* trig_count, int capacity, void* workspace, size_t workspace_bytes,
                             void* q_workspace, size_t q_workspace_bytes, void* stream);
 
+/* ---- whitening (replaces `whiten`, MLGWSC-1/inference.py:56-137, psd=None branch; pycbc 2.4.0 semantics) ----- */
+/* strain: device f64 [n] (one detector, n even).  Welch-median PSD over segments of seg_len samples every
+ * seg_stride (TimeSeries.psd(segment_duration): seg_len = round(0.5 s * fs) = 1024, stride seg_len/2), interpolated
+ * to the segment's resolution, inverse-spectrum truncation to max_filter_len taps (int(0.25 s * fs) = 512) with a
+ * Hann window (trunc_hann) above low_frequency_cutoff (<= 0: none), strain filtered with psd_trunc^-1/2 and -- if
+ * remove_corrupted -- cropped by max_filter_len/2 samples at both ends.
+ * Outputs (device; white and white_f32 optional, at least one): white f64 / white_f32 f32 [n - max_filter_len]
+ * (or [n]); psd_out (optional) f64 [seg_len/2 + 1] = the un-interpolated Welch PSD (`return_psd`).
+ * fir_half: half-length of the time-domain filter that applies psd_trunc^-1/2 (0 = default 8192, see whiten.cuh). */
+size_t gww_whiten_workspace_bytes(long n, int seg_len, int seg_stride, int max_filter_len, int fir_half);
+int gww_whiten(const double* strain, long n, double delta_t, int seg_len, int seg_stride, int max_filter_len,
+               double low_frequency_cutoff, int trunc_hann, int remove_corrupted, int fir_half, double* white,
+               float* white_f32, double* psd_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- building blocks exported for parity tests and profiling ----------------------------------- */
-/* C[M,N] = epilogue(A[M,K] * W[N,K]^T); A, W device bf16 row-major; epilogue ids as in
- * gemm_tc.cuh (0 bias->bf16, 1 bias+gelu->bf16, 2 bias+resid->f32, 3 bias+gelu+pos->f32). */
+/* C[M,N] = epilogue(A[M,K] * W[N,K]^T); A, W device 16-bit (gww_operand_dtype()) row-major; epilogue ids as in
+ * gemm_tc.cuh (0 bias->16-bit, 1 bias+gelu->16-bit, 2 bias+resid->f32, 3 bias+gelu+pos->f32).  (The name keeps
+ * its round-1 spelling; "bf16" here means "the 16-bit operand type of the build".) */
 int gww_gemm_bf16(const void* A, const void* W, void* C, const float* bias, const float* resid,
                   const float* pos, long M, int N, int K, int epilogue, int block_n, void* stream);
-/* qkv device bf16 [n, T, 3d] -> out device bf16 [n, T, d] */
+/* qkv device 16-bit [n, T, 3d] -> out device 16-bit [n, T, d] */
 int gww_attention(const void* qkv, void* out, long n, int T, int d_model, void* stream);
-/* x device f32 [rows, d] -> out bf16 (out_bf16=1) or f32 [rows, d] */
+/* x device f32 [rows, d] -> out 16-bit operand type (out_bf16=1) or f32 [rows, d] */
 int gww_layernorm(const float* x, void* out, const float* gamma, const float* beta, long rows, int d,
                   int out_bf16, void* stream);
 /* The reference consumes only last_hidden_state[:, -1, :]; by default the final encoder layer is

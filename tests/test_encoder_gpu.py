@@ -1,13 +1,19 @@
 """End-to-end parity of the B200 encoder / model path against the reference's PyTorch path
 (HF WhisperEncoder fp32 + unmerged DoRA + nn.Sequential head) on identical synthetic inputs.
-Gates (BASELINE.json north_star): logits within 2e-2 absolute, and -- because random-init logits
-barely move -- also within 5% of the oracle's own spread for the spread-scaled
-weight set."""
+Gates (BASELINE.json north_star): logits within 2e-2 absolute -- no escape clause; what PyTorch's own bf16
+autocast of the reference gives on the same inputs is printed as a diagnostic only -- and, because random-init
+logits barely move, the conditioned ("spread") weight sets of gw_whisper_b200.synthetic are used
+so that the tolerance is small against the oracle's own spread.  The full-size versions of these checks (2048 /
+512 windows, trigger and argmax agreement) are in tests/test_parity_configs_gpu.py."""
 import numpy as np
 import pytest
 import torch
 
+from parity_util import fp32_strict
+
 pytestmark = pytest.mark.gpu
+fp32_strict()
+HID_TOL = 2e-2      # final-LayerNorm hidden states are O(1): same absolute tolerance as the logits
 
 
 def _strain(n, D=1, seed=1234):
@@ -52,15 +58,14 @@ def test_encoder_last_hidden_state(size, spread):
     # token 1499 of the full computation up to summation order / bf16 rounding of that one row
     pooled = enc.pooled(feats.to(dev)).cpu()
     e_pool, _ = _stats(f"pooled(last token)[{size},spread={spread}] vs oracle", pooled, ref[:, -1])
-    assert (pooled - got[:, -1]).abs().max().item() < 3e-2
-    assert e_pool < 1.5 * yard.max().item() + 2e-2
+    assert (pooled - got[:, -1]).abs().max().item() < HID_TOL
+    assert e_pool < HID_TOL
     mean_pooled = enc.pooled(feats.to(dev), use_last_token=False).cpu()
     assert torch.allclose(mean_pooled, got.mean(1), atol=1e-4)
-    # LayerNorm'd outputs are O(1).  Gate: no worse than 1.5x PyTorch's own bf16 autocast of the
-    # reference model (+ a small floor), and mean error well inside the bf16 rounding level.
-    assert e < 1.5 * yard.max().item() + 2e-2, "encoder hidden states off"
-    assert (got - ref).abs().mean().item() < 1.5 * yard.mean().item() + 2e-3
-    assert e_last < 1.5 * yard.max().item() + 2e-2
+    # LayerNorm'd outputs are O(1): absolute gates on every token, the last token and the mean error
+    assert e < HID_TOL, "encoder hidden states off"
+    assert (got - ref).abs().mean().item() < 2e-3
+    assert e_last < HID_TOL
 
 
 def test_last_token_pruning_matches_full_final_layer():
@@ -87,7 +92,7 @@ def test_last_token_pruning_matches_full_final_layer():
     e_p, _ = _stats("pooled pruned vs fp32 oracle", pruned, ref)
     e_f, _ = _stats("pooled full vs fp32 oracle", full, ref)
     assert torch.equal(full, from_hidden)
-    assert e_pf < 3e-2 and e_p < 1.2 * max(e_f, 2e-2)
+    assert e_pf < HID_TOL and e_p < HID_TOL and e_f < HID_TOL
 
 
 def test_encoder_rejects_bad_length():
@@ -127,10 +132,8 @@ def test_two_channel_model_with_dora(spread):
     e1, sp = _stats(f"two_channel fused logits (spread={spread})", got_fused, ref)
     e2, _ = _stats(f"two_channel module logits (spread={spread})", got_mod, ref)
     yard = (_bf16_yardstick(ref_model.to(dev), feats[:, 0].to(dev), feats[:, 1].to(dev)).cpu() - ref).abs().max().item()
-    print(f"torch bf16-autocast yardstick on logits: {yard:.4e}")
-    # 2e-2 absolute, or -- when PyTorch's own bf16 autocast of the reference model is already at that
-    # level on these (deliberately ill-conditioned, spread-scaled) weights -- within 1.5x of it
-    assert (e1 < 2e-2 and e2 < 2e-2) or max(e1, e2) < 1.5 * yard
+    print(f"diagnostic only: torch bf16-autocast of the oracle is off by {yard:.4e} on these logits")
+    assert e1 < 2e-2 and e2 < 2e-2
     if spread:
         assert sp > 5e-3, "spread-scaled weights should give logits that move with the input"
     # thresholded decisions agree away from a guard band around the threshold
@@ -164,8 +167,8 @@ def test_glitch_small_multiclass_argmax():
     got = model(logmel_features(strain[:, 0].to(dev))).cpu()
     e, sp = _stats("glitch small logits", got, ref)
     yard = (_bf16_yardstick(ref_model.to(dev), feats.to(dev)).cpu() - ref).abs().max().item()
-    print(f"torch bf16-autocast yardstick on logits: {yard:.4e}")
-    assert e < 2e-2 or e < 1.5 * yard
+    print(f"diagnostic only: torch bf16-autocast of the oracle is off by {yard:.4e} on these logits")
+    assert e < 2e-2
     top2 = ref.topk(2, dim=1).values
     decisive = (top2[:, 0] - top2[:, 1]) > 4e-2
     assert torch.equal(got.argmax(1)[decisive], ref.argmax(1)[decisive])

@@ -105,11 +105,12 @@ def test_segment_slicer_matches_reference(n_samples):
     assert len(extract_segments(h1)) == len(ours)
 
 
-def test_slicer_requires_whitened_input():
+def test_slicer_whitening_needs_the_gpu_and_start_times_must_agree():
     from gw_whisper_b200.inference import ArrayFile, SegmentSlicer
     f = ArrayFile.from_segments({"H1": {"0": np.zeros(4096)}, "L1": {"0": np.zeros(4096)}}, {"0": 0.0})
-    with pytest.raises(NotImplementedError):
-        SegmentSlicer(f, "0", white=False)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):        # white=False whitens on the GPU: no device, no silent CPU path
+            SegmentSlicer(f, "0", white=False)
     with pytest.raises(AssertionError):
         g = ArrayFile.from_segments({"H1": {"0": np.zeros(4096)}}, {"0": 0.0})
         g["L1"] = ArrayFile.from_segments({"L1": {"0": np.zeros(4096)}}, {"0": 1.0})["L1"]

@@ -55,8 +55,8 @@ def test_gemm_tcgen05(lib, M, N, K, epi, bn):
     from gw_whisper_b200 import _lib
     dev = _cuda()
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + epi)
-    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
-    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    A = torch.randn(M, K, generator=g).to(dev).to(_lib.operand_dtype())
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).to(_lib.operand_dtype())
     bias = torch.randn(N, generator=g).to(dev)
     resid = torch.randn(M, N, generator=g).to(dev) if epi == 2 else None
     pos = torch.randn(M, N, generator=g).to(dev) if epi == 3 else None
@@ -70,7 +70,7 @@ def test_gemm_tcgen05(lib, M, N, K, epi, bn):
     else:
         ref = _gelu(acc) + pos
     out_f32 = epi in (2, 3)
-    C = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    C = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32 if out_f32 else _lib.operand_dtype())
     rc = lib.gww_gemm_bf16(A.data_ptr(), W.data_ptr(), C.data_ptr(), bias.data_ptr(), _lib.ptr(resid),
                            _lib.ptr(pos), M, N, K, epi, bn, _lib.stream_ptr())
     _lib.check(rc)
@@ -87,8 +87,8 @@ def test_gemm_inplace_residual(lib):
     dev = _cuda()
     g = torch.Generator().manual_seed(5)
     M, N, K = 2500, 512, 512
-    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
-    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    A = torch.randn(M, K, generator=g).to(dev).to(_lib.operand_dtype())
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).to(_lib.operand_dtype())
     bias = torch.randn(N, generator=g).to(dev)
     x = torch.randn(M, N, generator=g).to(dev)
     ref = x + A.float() @ W.float().t() + bias
@@ -109,7 +109,7 @@ def test_layernorm(lib, d, out_bf16):
     gamma = torch.randn(d, generator=g).to(dev)
     beta = torch.randn(d, generator=g).to(dev)
     ref = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5)
-    out = torch.empty(rows, d, device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    out = torch.empty(rows, d, device=dev, dtype=_lib.operand_dtype() if out_bf16 else torch.float32)
     _lib.check(lib.gww_layernorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, d,
                                  out_bf16, _lib.stream_ptr()))
     torch.cuda.synchronize()
@@ -140,10 +140,10 @@ def test_attention_tcgen05(lib, n, T, d, scale):
     g = torch.Generator().manual_seed(n * 100 + T + d)
     qkv = torch.randn(n, T, 3 * d, generator=g)
     qkv[:, :, :d] *= scale / 8.0
-    qkv = qkv.to(dev).bfloat16()
+    qkv = qkv.to(dev).to(_lib.operand_dtype())
     # make later keys progressively larger for one case so the running max keeps growing
     ref = _attn_ref(qkv, d)
-    out = torch.full((n, T, d), float("nan"), device=dev, dtype=torch.bfloat16)
+    out = torch.full((n, T, d), float("nan"), device=dev, dtype=_lib.operand_dtype())
     _lib.check(lib.gww_attention(qkv.data_ptr(), out.data_ptr(), n, T, d, _lib.stream_ptr()))
     torch.cuda.synchronize()
     _report(f"attn{(n, T, d, scale)}", out.float(), ref, 2e-2, 2e-2)
@@ -159,9 +159,9 @@ def test_attention_growing_max(lib):
     ramp = torch.linspace(0.2, 6.0, T).view(1, T, 1)
     qkv[:, :, d:2 * d] = qkv[:, :, d:2 * d].abs() * ramp        # k grows with position
     qkv[:, :, :d] = qkv[:, :, :d].abs() * 0.5                    # q positive -> scores grow
-    qkv = qkv.to(dev).bfloat16()
+    qkv = qkv.to(dev).to(_lib.operand_dtype())
     ref = _attn_ref(qkv, d)
-    out = torch.full((n, T, d), float("nan"), device=dev, dtype=torch.bfloat16)
+    out = torch.full((n, T, d), float("nan"), device=dev, dtype=_lib.operand_dtype())
     _lib.check(lib.gww_attention(qkv.data_ptr(), out.data_ptr(), n, T, d, _lib.stream_ptr()))
     torch.cuda.synchronize()
     _report("attn_growing", out.float(), ref, 2e-2, 2e-2)
@@ -185,6 +185,48 @@ def test_logmel_frontend_vs_oracle(lib):
         print(f"logmel window {i}: normalised err {e:.3e}  tail const {np.ptp(got[i][:, 102:]):.1e}")
         assert e <= 1e-4
     assert np.array_equal(got[:, :, 102:], np.broadcast_to(got[:, :, 102:103], got[:, :, 102:].shape))
+
+
+def test_resample_and_logmel_from_16k_match_the_reference_calls(lib):
+    """The two halves of front end A as the reference's datasets use them: the stored audio is
+    scipy.signal.resample(x, 16000) (preprocess.py:44-51, f32 at :95) and the features are
+    WhisperFeatureExtractor(audio, sampling_rate=16000) per item (dataset.py:20-24)."""
+    from scipy.signal import resample
+    from transformers import WhisperFeatureExtractor
+    from oracle import logmel as L
+    from gw_whisper_b200 import LogMelFeatureExtractor, logmel_features, resample_timeseries
+    dev = _cuda()
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((4, 2048)).astype(np.float32)
+    x[2] *= 1e-3
+    want_audio = np.stack([resample(xi.astype(np.float64), 16000) for xi in x]).astype(np.float32)
+    got_audio = resample_timeseries(x)                       # numpy in -> numpy out, like the reference function
+    assert got_audio.shape == (4, 16000) and got_audio.dtype == np.float32
+    e_a = np.abs(got_audio - want_audio).max() / np.abs(want_audio).max()
+    print(f"resample_timeseries vs scipy.signal.resample: normalised err {e_a:.3e}")
+    assert e_a <= 2e-7                                       # f32 storage rounding
+    t_audio = resample_timeseries(torch.from_numpy(x).to(dev))
+    assert t_audio.is_cuda and np.array_equal(t_audio.cpu().numpy(), got_audio)
+    # features from the REFERENCE's stored audio through the HF extractor vs ours from the same audio
+    hf = WhisperFeatureExtractor()
+    want = np.stack([hf(a, sampling_rate=16000, return_tensors="np").input_features[0] for a in want_audio])
+    fe = LogMelFeatureExtractor.from_pretrained("openai/whisper-tiny")
+    got = fe(want_audio, sampling_rate=16000, return_tensors="pt").input_features
+    assert got.shape == (4, 80, 3000) and got.is_cuda
+    for i in range(4):
+        e = L.feature_error(got[i].cpu().numpy(), want[i])
+        print(f"logmel_from_16k window {i}: normalised err vs HF WhisperFeatureExtractor {e:.3e}")
+        assert e <= 1e-4
+    one = fe(want_audio[0], sampling_rate=16000).input_features   # 1-D item, as Dataset.__getitem__ passes it
+    assert one.shape == (1, 80, 3000) and torch.equal(one[0], got[0])
+    # fused kernel == the two halves chained (same arithmetic, same f32 rounding of the audio)
+    fused = logmel_features(torch.from_numpy(x).to(dev))
+    chained = fe(torch.from_numpy(got_audio).to(dev), sampling_rate=16000).input_features
+    assert torch.equal(fused, chained)
+    with pytest.raises(ValueError):
+        fe(want_audio, sampling_rate=8000)
+    with pytest.raises(ValueError):
+        fe(np.zeros(12345, dtype=np.float32), sampling_rate=16000)
 
 
 def test_head_and_compaction(lib):

@@ -21,6 +21,8 @@ class FakeNetwork:
     the samples the shard must own (halo included)."""
 
     def stream_search(self, strain, hop, n_windows, thr, first_window=0):
+        # a shard is handed exactly its sample range plus the halo, never the whole segment (ADVICE r1)
+        assert first_window == 0 and strain.shape[1] == (n_windows - 1) * hop + 2048
         k = torch.arange(first_window, first_window + n_windows)
         idx = k[:, None] * hop + torch.arange(2048)[None, :]
         scores = strain[0][idx].double().mean(dim=1).float()

@@ -23,8 +23,8 @@ a = ap.parse_args()
 lib = _lib.load()
 dev = torch.device("cuda:0")
 n, T, d = a.det_windows, a.T, a.d
-qkv = (torch.randn(n, T, 3 * d, device=dev) * a.scale).bfloat16()
-out = torch.empty(n, T, d, device=dev, dtype=torch.bfloat16)
+qkv = (torch.randn(n, T, 3 * d, device=dev) * a.scale).to(_lib.operand_dtype())
+out = torch.empty(n, T, d, device=dev, dtype=_lib.operand_dtype())
 
 
 def run():

@@ -37,11 +37,11 @@ res = {}
 for name, (N, K, epi) in shapes.items():
     if only and name not in only:
         continue
-    A = torch.randn(M, K, device=dev).bfloat16()
-    W = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    A = torch.randn(M, K, device=dev).to(_lib.operand_dtype())
+    W = (torch.randn(N, K, device=dev) / K ** 0.5).to(_lib.operand_dtype())
     bias = torch.randn(N, device=dev)
     out_f32 = epi in (2, 3)
-    Cm = torch.empty(M, N, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    Cm = torch.empty(M, N, device=dev, dtype=torch.float32 if out_f32 else _lib.operand_dtype())
     resid = torch.randn(M, N, device=dev) if epi == 2 else None
     bn = a.bn or (256 if N % 256 == 0 else (192 if N % 192 == 0 else 128))
 
