@@ -634,7 +634,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the mlgwsc (configs[3], sharded over the ranks) and glitch_small (configs[2]) sub-records")
     ap.add_argument("--mlgwsc-scale", type=float, default=1.0, help="scale of the one-hour MLGWSC-1 stream (tests: 0.02)")
-    ap.add_argument("--mlgwsc-ref-windows", type=int, default=12, help="windows of the MLGWSC-1 CPU baseline sample")
+    ap.add_argument("--mlgwsc-ref-windows", type=int, default=96, help="windows of the MLGWSC-1 CPU baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

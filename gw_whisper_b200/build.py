@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgww_b200.so")
 LIB_BF16 = os.path.join(HERE, "libgww_b200_bf16.so")
 SOURCES = ["gww_api.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attention_tc.cuh", "attention_persist.cuh", "elementwise.cuh", "logmel.cuh", "qfront.cuh", "whiten.cuh",
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attention_tc.cuh", "attention_persist.cuh", "elementwise.cuh", "logmel.cuh", "qfront.cuh", "whiten.cuh", "qadapter_tc.cuh",
            os.path.join("..", "..", "include", "gww.h")]
 
 

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -19,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "logmel.cuh"
 #include "qfront.cuh"
+#include "qadapter_tc.cuh"
 #include "whiten.cuh"
 
 using namespace gww;
@@ -1410,6 +1412,19 @@ extern "C" int gww_qfront_set_adapter(gww_qfront_t* qf, const gww_qadapter_weigh
   GWW_TRY(qf_upload(qf, w2, &ad.w2)); GWW_TRY(qf_upload(qf, b2, &ad.b2));
   GWW_TRY(qf_upload(qf, w3, &ad.w3)); GWW_TRY(qf_upload(qf, b3, &ad.b3));
   GWW_TRY(qf_upload(qf, w4, &ad.w4));
+  {  // bf16 hi/lo images of the conv2 / conv3 weights in the UMMA canonical layout (tensor-core path)
+    uint4 *p2 = nullptr, *p3 = nullptr;
+    CU_TRY(cudaMalloc(&p2, (size_t)QtCfg<16, 32>::kWBytes));
+    qf->owned.push_back(p2);
+    CU_TRY(cudaMalloc(&p3, (size_t)QtCfg<32, 64>::kWBytes));
+    qf->owned.push_back(p3);
+    qt_pack_weights_kernel<16, 32><<<(QtCfg<16, 32>::kWElems + 255) / 256, 256>>>(ad.w2, p2);
+    LAUNCH_CHECK();
+    qt_pack_weights_kernel<32, 64><<<(QtCfg<32, 64>::kWElems + 255) / 256, 256>>>(ad.w3, p3);
+    LAUNCH_CHECK();
+    CU_TRY(cudaDeviceSynchronize());
+    ad.w2p = p2; ad.w3p = p3;
+  }
   ad.b4 = w->conv4_b[0];
   ad.scale = w->scale; ad.bias = w->bias;
   for (int i = 0; i < 8; ++i) { ad.gamma[i] = 1.f; ad.beta[i] = 0.f; }
@@ -1475,6 +1490,16 @@ static int run_qscan(const gww_qfront* qf, const float* strain, long n, long win
   return GWW_OK;
 }
 
+// tensor-core convolutions (default) vs the fp32 CUDA-core kernels of round 1 (GWW_QADAPTER_TC=0)
+static bool qadapter_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GWW_QADAPTER_TC");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // adapter CNN on spec [n,F,T] -> f32 [n,80,3000] and/or bf16 time-major rows of feats_tm
 static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det, float* feats_f32,
                         op16_t* feats_tm, long tm_stride_w, long tm_off, const QWorkspace& ws,
@@ -1483,12 +1508,34 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
   if (det < 0 || det >= qf->n_detectors) return fail(GWW_ERR_INVALID, "qadapter: det_idx=%d out of range", det);
   const int F = qf->spec_f, T = qf->spec_t;
   ProfScope ps(PK_QADAPTER, s);
-  qadapter_conv1_kernel<<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
-  LAUNCH_CHECK();
-  qadapter_conv2_kernel<<<dim3(T / 32, F / 32, (unsigned)n), 256, kC2SmemBytes, s>>>(ws.act1, ws.act2, F / 2, T / 2, qf->ad);
-  LAUNCH_CHECK();
-  qadapter_conv3_kernel<<<dim3(T / 64, F / 64, (unsigned)n), 256, kC3SmemBytes, s>>>(ws.act2, ws.map, F / 4, T / 4, qf->ad);
-  LAUNCH_CHECK();
+  if (qadapter_tc_enabled() && F % 64 == 0 && T % 32 == 0) {
+    // tensor-core path: conv1 (CUDA cores, fp32) writes bf16 hi/lo planes; conv2 / conv3 are tcgen05 implicit GEMMs
+    qadapter_conv1_kernel<true><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
+    LAUNCH_CHECK();
+    using C2 = QtCfg<16, 32>;
+    using C3 = QtCfg<32, 64>;
+    auto k2 = qadapter_conv_tc_kernel<16, 32, 0>;
+    auto k3 = qadapter_conv_tc_kernel<32, 64, 1>;
+    GWW_TRY(ensure_smem_attr(k2, C2::kSmemBytes));
+    GWW_TRY(ensure_smem_attr(k3, C3::kSmemBytes));
+    const long tiles2 = (long)(F / 2 / kQtTileH) * (T / 2 / kQtTileW) * n, tiles3 = (long)(F / 4 / kQtTileH) * (T / 4 / kQtTileW) * n;
+    const int sms = g_num_sms;
+    const int grid2 = (int)std::min<long>(sms, (tiles2 + C2::kGroups - 1) / C2::kGroups);
+    const int grid3 = (int)std::min<long>(sms, (tiles3 + C3::kGroups - 1) / C3::kGroups);
+    k2<<<grid2, C2::kThreads, C2::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act1), qf->ad.w2p, qf->ad.b2, nullptr, 0.f,
+                                                  ws.act2, F / 2, T / 2, n);
+    LAUNCH_CHECK();
+    k3<<<grid3, C3::kThreads, C3::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act2), qf->ad.w3p, qf->ad.b3, qf->ad.w4,
+                                                  qf->ad.b4, ws.map, F / 4, T / 4, n);
+    LAUNCH_CHECK();
+  } else {
+    qadapter_conv1_kernel<false><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
+    LAUNCH_CHECK();
+    qadapter_conv2_kernel<<<dim3(T / 32, F / 32, (unsigned)n), 256, kC2SmemBytes, s>>>(ws.act1, ws.act2, F / 2, T / 2, qf->ad);
+    LAUNCH_CHECK();
+    qadapter_conv3_kernel<<<dim3(T / 64, F / 64, (unsigned)n), 256, kC3SmemBytes, s>>>(ws.act2, ws.map, F / 4, T / 4, qf->ad);
+    LAUNCH_CHECK();
+  }
   qadapter_pool_kernel<<<dim3((GWW_N_FRAMES + 127) / 128, (unsigned)n), 256, 0, s>>>(
       ws.map, feats_f32, feats_tm, tm_stride_w, tm_off, F / 4, T / 4, GWW_N_MELS, GWW_N_FRAMES, det, qf->ad);
   LAUNCH_CHECK();
@@ -1586,7 +1633,7 @@ extern "C" int gww_stream_search_qscan(const gww_model_t* m, const gww_qfront_t*
 // ------------------------------------------------------------------------------------------------
 struct WhitenPlan {
   long n, n_seg, first, nk;
-  int seg_len, log2n, seg_stride, nb, L, H, cs_chunks;
+  int seg_len, log2n, seg_stride, nb, L, H, cs_chunks, wrap;
   // workspace
   double2* tw; double *seg_psd, *psd0, *inv_asd, *mag, *partial, *q, *qt, *w;
   size_t total;
@@ -1614,8 +1661,11 @@ static int whiten_plan(long n, int seg_len, int seg_stride, int max_filter_len, 
   pl->L = max_filter_len;
   long H = fir_half > 0 ? fir_half : 8192;
   if (H < max_filter_len / 2) H = max_filter_len / 2;
-  if (H > n / 2 - 1) H = n / 2 - 1;
   if (H > 11264) H = 11264;                  // shared-memory tile of the FIR: (2048 + 2H) * 9/8 doubles <= 227 KB
+  // short segment: the filter covers the whole circle and the result is exact; the taps -n/2 and +n/2 are the
+  // same sample, so w[n/2] is halved (pl->wrap)
+  pl->wrap = 0;
+  if (H >= n / 2) { H = n / 2; pl->wrap = 1; }
   pl->H = (int)H;
   pl->cs_chunks = (int)((pl->nk + kCsChunk - 1) / kCsChunk);
   size_t off = 0;
@@ -1694,7 +1744,7 @@ extern "C" int gww_whiten(const double* strain, long n, double delta_t, int seg_
   const int nq = pl.L / 2 + 1;
   cosine_series_kernel<<<dim3(pl.cs_chunks, (nq + kCsThreads - 1) / kCsThreads), kCsThreads, 0, s>>>(pl.inv_asd, pl.nk, n, nq, pl.partial);
   LAUNCH_CHECK();
-  cosine_series_reduce_kernel<<<(nq + 255) / 256, 256, 0, s>>>(pl.partial, pl.cs_chunks, nq, 1.0 / (double)n, pl.q);
+  cosine_series_reduce_kernel<<<(nq + 255) / 256, 256, 0, s>>>(pl.partial, pl.cs_chunks, nq, 1.0 / (double)n, pl.q, -1);
   LAUNCH_CHECK();
   trunc_window_kernel<<<(pl.L + 255) / 256, 256, 0, s>>>(pl.q, pl.L, trunc_hann, pl.qt);
   LAUNCH_CHECK();
@@ -1706,7 +1756,8 @@ extern "C" int gww_whiten(const double* strain, long n, double delta_t, int seg_
   const int nw = pl.H + 1;
   cosine_series_kernel<<<dim3(pl.cs_chunks, (nw + kCsThreads - 1) / kCsThreads), kCsThreads, 0, s>>>(pl.mag, pl.nk, n, nw, pl.partial);
   LAUNCH_CHECK();
-  cosine_series_reduce_kernel<<<(nw + 255) / 256, 256, 0, s>>>(pl.partial, pl.cs_chunks, nw, 1.0 / (double)n, pl.w);
+  cosine_series_reduce_kernel<<<(nw + 255) / 256, 256, 0, s>>>(pl.partial, pl.cs_chunks, nw, 1.0 / (double)n, pl.w,
+                                                                pl.wrap ? nw - 1 : -1);
   LAUNCH_CHECK();
   const long n0 = remove_corrupted ? pl.L / 2 : 0;
   const long n_out = remove_corrupted ? n - pl.L : n;

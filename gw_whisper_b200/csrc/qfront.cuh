@@ -386,6 +386,8 @@ qscan_interp_kernel(const float* __restrict__ tiles, const unsigned int* __restr
 // ------------------------------------------------------------------------------------------------
 // Q-Adapter CNN (MLGWSC-1/inference.py:322-351)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo);   // qadapter_tc.cuh
+
 struct QAdapterDev {
   const float* w1;   // [9][16]          conv1 weight, tap-major
   const float* b1;   // [16]
@@ -394,6 +396,8 @@ struct QAdapterDev {
   const float* w3;   // [9][32][64]
   const float* b3;   // [64]
   const float* w4;   // [64]             conv 1x1
+  const uint4* w2p;  // conv2 / conv3 weights packed for the tensor-core path (qadapter_tc.cuh), or nullptr
+  const uint4* w3p;
   float b4;
   float scale, bias;
   float gamma[8], beta[8];
@@ -401,6 +405,9 @@ struct QAdapterDev {
 
 // conv3x3(1->16, pad 1) + ReLU + maxpool2 : spec [n,H,W] -> act1 [n,H/2,W/2,16] (NHWC)
 // CTA = 16x16 pooled pixels (32x32 conv pixels); one thread per pooled pixel, 16 channels.
+// PLANES: store act1 in the plane format of the tensor-core convolutions (qadapter_tc.cuh): [n][4][H/2][W/2] x 16 B,
+// planes = bf16 hi of channels 0-7, hi 8-15, lo 0-7, lo 8-15 (lo = bf16(v - hi)).
+template <bool PLANES>
 __global__ void __launch_bounds__(256, 4)
 qadapter_conv1_kernel(const float* __restrict__ spec, float* __restrict__ act1, int H, int W,
                       const QAdapterDev ad) {
@@ -475,9 +482,21 @@ qadapter_conv1_kernel(const float* __restrict__ spec, float* __restrict__ act1, 
     }
   }
   const int PH = H >> 1, PW = W >> 1;
-  float4* dst = reinterpret_cast<float4*>(act1 + ((n * PH + (py0 + ly)) * static_cast<long>(PW) + (px0 + lx)) * 16);
+  if constexpr (PLANES) {
+    uint4* dst = reinterpret_cast<uint4*>(act1) + n * 4L * PH * PW + static_cast<long>(py0 + ly) * PW + (px0 + lx);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    for (int hc = 0; hc < 2; ++hc) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_bf16x2(o[8 * hc + 2 * e], o[8 * hc + 2 * e + 1], hi[e], lo[e]);
+      dst[static_cast<long>(hc) * PH * PW] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      dst[static_cast<long>(2 + hc) * PH * PW] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(act1 + ((n * PH + (py0 + ly)) * static_cast<long>(PW) + (px0 + lx)) * 16);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+  }
 }
 
 // conv3x3(16->32, pad 1) + ReLU + maxpool2 : act1 [n,H,W,16] -> act2 [n,H/2,W/2,32]

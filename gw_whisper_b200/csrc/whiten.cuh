@@ -18,8 +18,9 @@
 //      data, any even length).  |Q| is smooth except for kinks where the truncated filter changes sign below the
 //      cut-off, so w = irfft(|Q|) decays like 1/m^2 (3e-6 of its peak beyond L/2, 4e-9 beyond 8192 taps): the
 //      product is applied as a circular FIR with w truncated to +-H taps.  H = 8192: max deviation from the
-//      N-point-FFT result 4e-5 of the output's rms on detector-like noise, all of it below the cut-off
-//      frequency (measured in tests/test_whiten.py; above 30 Hz the two agree to 1e-7)
+//      N-point-FFT result 4e-5 of the output's rms on detector-like noise with 40x spectral lines, most of it
+//      below the cut-off frequency (measured in tests/test_whiten.py: 8e-6 above 30 Hz); segments shorter than
+//      2H samples are covered entirely and agree to 5e-12
 //                                                            cosine_series_kernel + fir_apply_kernel
 //   6. crop L/2 samples at both ends (remove_corrupted).
 #pragma once
@@ -196,12 +197,12 @@ cosine_series_kernel(const double* __restrict__ a, long nk, long N, int n_out, d
 }
 
 __global__ void cosine_series_reduce_kernel(const double* __restrict__ partial, int n_chunks, int n_out, double inv_n,
-                                            double* __restrict__ y) {
+                                            double* __restrict__ y, int halve_index) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_out) return;
   double acc = 0.0;
   for (int c = 0; c < n_chunks; ++c) acc += partial[(long)c * n_out + m];
-  y[m] = acc * inv_n;
+  y[m] = acc * inv_n * (m == halve_index ? 0.5 : 1.0);
 }
 
 // Hann truncation of q (inverse_spectrum_truncation): q is even, q[0..L/2] given.

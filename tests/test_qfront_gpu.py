@@ -112,8 +112,42 @@ def test_qadapter_features_vs_oracle():
         y = (ref.scale * y + ref.bias) * ref.film_gamma[1] + ref.film_beta[1]
     got2 = ours.adapt(spec.cuda(), 1).cpu()
     e2 = _nerr(got2, y)
-    print(f"qadapter CNN alone: normalised error {e2:.3e}")
-    assert e2 <= 2e-5
+    print(f"qadapter CNN alone (tensor-core convolutions, bf16 hi/lo split): normalised error {e2:.3e}")
+    assert e2 <= 4e-5
+
+
+def test_qadapter_fp32_cuda_core_path_still_matches(tmp_path):
+    """GWW_QADAPTER_TC=0 selects the round-1 fp32 CUDA-core convolutions (read once per process -> child process);
+    they must agree with the oracle to fp32 accuracy and with the tensor-core path to its split precision."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = _seeded_adapter()
+    sd = str(tmp_path / "adapter.pt")
+    torch.save({k: v for k, v in ref.state_dict().items() if not k.startswith("q_transform.")}, sd)
+    x = _strain(3, 2, seed=8)
+    with torch.no_grad():
+        spec = ref.q_transform(x[:, 1]).reshape(3, 512, 512)
+        y = ref.freq_adapter(spec.unsqueeze(1))
+        y = ref.final_pool(y).squeeze(1)
+        want = (ref.scale * y + ref.bias) * ref.film_gamma[1] + ref.film_beta[1]
+    torch.save(spec, str(tmp_path / "spec.pt"))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from gw_whisper_b200 import QTransformAdapter\n"
+        "a = QTransformAdapter(n_detectors=2); a.load_state_dict(torch.load(sys.argv[1]))\n"
+        "torch.save(a.adapt(torch.load(sys.argv[2]).cuda(), 1).cpu(), sys.argv[3])\n")
+    outs = {}
+    for tc in ("0", "1"):
+        out = str(tmp_path / f"out{tc}.pt")
+        subprocess.run([sys.executable, "-c", code, sd, str(tmp_path / "spec.pt"), out], check=True,
+                       env={**os.environ, "GWW_QADAPTER_TC": tc}, timeout=600)
+        outs[tc] = torch.load(out)
+    e0, e1, e01 = _nerr(outs["0"], want), _nerr(outs["1"], want), _nerr(outs["1"], outs["0"])
+    print(f"adapter CNN vs oracle: fp32 CUDA-core path {e0:.3e}, tensor-core path {e1:.3e}; between them {e01:.3e}")
+    assert e0 <= 5e-6 and e1 <= 4e-5 and e01 <= 4e-5
 
 
 def _reference_model(base, dora, adapter, num_classes=2, use_last_token=True):
