@@ -618,6 +618,27 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_single(args):
+    """One sub-record alone (ncu / tuning runs): same code path as inside the full line."""
+    import torch
+    import torch.distributed as dist
+    from gw_whisper_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    rec = mlgwsc_record(args, dev, rank, world, lib) if args.workload == "mlgwsc" else glitch_record(args, dev, lib)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -631,6 +652,9 @@ def main():
                          "front end and 96 attention work items per SM; measured 217.8 vs 222.5 ms per step for 256)")
     ap.add_argument("--ref-windows", type=int, default=40, help="windows per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="all", choices=["all", "mlgwsc", "glitch"],
+                    help="all = headline line with the sub-records; mlgwsc / glitch = that sub-record alone as the line "
+                         "(profiling runs)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the mlgwsc (configs[3], sharded over the ranks) and glitch_small (configs[2]) sub-records")
     ap.add_argument("--mlgwsc-scale", type=float, default=1.0, help="scale of the one-hour MLGWSC-1 stream (tests: 0.02)")
@@ -638,6 +662,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "all":
+        run_single(args)
     else:
         run_b200(args)
 

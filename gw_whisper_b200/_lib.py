@@ -51,7 +51,7 @@ class QAdapterWeights(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "conv3_w", "conv3_b",
                                           "conv4_w", "conv4_b")] + [
         ("scale", C.c_float), ("bias", C.c_float), ("n_detectors", C.c_int),
-        ("film_gamma", c_float_p), ("film_beta", c_float_p)]
+        ("film_gamma", c_float_p), ("film_beta", c_float_p), ("c1", C.c_int), ("c2", C.c_int), ("c3", C.c_int)]
 
 
 # every symbol include/gww.h declares: (restype, argtypes)
@@ -64,6 +64,7 @@ SYMBOLS = {
     "gww_model_create": (_i, [C.POINTER(EncoderConfig), C.POINTER(EncoderWeights), C.POINTER(_vp)]),
     "gww_model_set_head": (_i, [_vp, C.POINTER(HeadWeights)]),
     "gww_model_destroy": (None, [_vp]),
+    "gww_model_ln_fold_state": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "gww_workspace_bytes": (_sz, [_vp, _i]),
     "gww_logmel_frontend": (_i, [_vp, _l, _vp, _vp]),
     "gww_resample_16k": (_i, [_vp, _l, _vp, _vp]),

@@ -30,13 +30,19 @@ def build_lib(force: bool = False, verbose: bool = False, bf16: bool = False) ->
     """Builds libgww_b200.so (fp16 tensor-core operands, the default) or, with bf16=True,
     libgww_b200_bf16.so (bf16 operands; selected at run time with GWW_OPERAND=bf16)."""
     lib = LIB_BF16 if bf16 else LIB
+    # tuning builds: extra -D switches into another file (selected at run time with GWW_LIB=<path>)
+    extra = os.environ.get("GWW_BUILD_DEFS", "").split()
+    if extra:
+        lib = os.environ.get("GWW_BUILD_OUT") or os.path.join(HERE, "variants", "libgww_variant.so")
+        os.makedirs(os.path.dirname(lib), exist_ok=True)
+        force = True
     if not force and not _stale(lib):
         return lib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [
         nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "--shared", "-Xcompiler", "-fPIC", "-o", lib,
-    ] + (["-DGWW_OPERAND_BF16=1"] if bf16 else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    ] + (["-DGWW_OPERAND_BF16=1"] if bf16 else []) + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -50,6 +50,12 @@ constexpr int kApLookahead = GWW_AP_LOOKAHEAD;
 #ifndef GWW_AP_PACKED_F32
 #define GWW_AP_PACKED_F32 1   // scale-subtract and row-sum on packed fp32 pairs (FFMA2 / FADD2)
 #endif
+// Of every 8 consecutive pairs of scores, GWW_AP_POLY pairs take their exponentials from the FMA pipe
+// (poly_exp2_pair) instead of MUFU.EX2: the kernel is bound by the XU pipe (MUFU.EX2 16 / clk / SM, r1 ncu: XU 68 %,
+// tensor 34 %), the fp32 pipe has slack.  Not used in the masked last key tile (-inf scores).  0 = all MUFU.
+#ifndef GWW_AP_POLY
+#define GWW_AP_POLY 0
+#endif
 #ifndef GWW_ATTN_POLL_NS
 #define GWW_ATTN_POLL_NS 64   // back-off of the MMA warp's polling loop when nothing is ready
 #endif
@@ -362,8 +368,13 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
 #if GWW_AP_PACKED_F32
           float x0, x1;                              // FFMA2 / FADD2: half the fp32-pipe instructions
           ffma2_bcast(x0, x1, __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]), kLog2e, mneg_g);
-          const float p0 = fast_exp2(x0);
-          const float p1 = fast_exp2(x1);
+          float p0, p1;
+          if (!kMask && GWW_AP_POLY > 0 && ((i >> 1) & 7) < GWW_AP_POLY) {
+            poly_exp2_pair(f2_pack(fmaxf(x0, -125.f), fmaxf(x1, -125.f)), p0, p1);
+          } else {
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+          }
           fadd2_acc(l0, l1, p0, p1);
 #else
           const float p0 = fast_exp2(fmaf(__uint_as_float(s[c][i]), kLog2e, mneg_g));

@@ -62,6 +62,9 @@ struct GemmParams {
   int stat_slots;        // partial slots per row written (producer) / to be summed (consumer)
   float ln_inv_k;        // 1 / d_model
   float ln_eps;
+  float* ln_guard;       // device float (bits compared as uint): running max of |mean| / std over the rows consumed,
+  float ln_guard_min;    //   recorded only above ln_guard_min (the fold loses precision when the residual stream has
+                         //   a large common mode; the host switches the model to the stand-alone LayerNorm then)
 };
 
 // LayerNorm folding.  h = LN(x) feeds only a Linear: LN(x) W^T + b = rs * (x (g.W)^T) - rs * mu * c1 + c2 with
@@ -379,6 +382,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float rs = rsqrtf(var + p.ln_eps);
           rs2 = f2_pack(rs, rs);
           nmr2 = f2_pack(-rs * mu, -rs * mu);
+          if (p.ln_guard != nullptr && n_idx == 0 && half == 0 && lane < rows_here) {
+            const float ratio = fabsf(mu) * rs;
+            if (ratio > p.ln_guard_min) atomicMax(reinterpret_cast<unsigned int*>(p.ln_guard), __float_as_uint(ratio));
+          }
         }
       }
       mbar_wait(bar_tfull + 8 * as, aphase);

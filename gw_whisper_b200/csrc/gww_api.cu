@@ -405,7 +405,12 @@ struct LnFold {
   const float* c1 = nullptr;
   int in_slots = 0;     // slots the producer of stats_in wrote
   int d_model = 0;
+  float* guard = nullptr;
 };
+// |mean| / std of a residual row above which the folded LayerNorm is considered unsafe (validated up to 1.2 on
+// random-init weights in round 1; the operand rounding of x, 2^-12 for fp16 / 2^-9 for bf16 relative to |mean|, is
+// amplified by this ratio in the normalised value)
+constexpr float kLnGuardLimit = GWW_OPERAND_BF16 ? 1.5f : 4.0f;
 static int stat_slots_of(int n, int block_n) { return 2 * ((n + block_n - 1) / block_n); }
 static void apply_fold(GemmParams& p, const LnFold& lf, int block_n) {
   p.xb = lf.xb;
@@ -415,6 +420,8 @@ static void apply_fold(GemmParams& p, const LnFold& lf, int block_n) {
   p.stat_slots = lf.stats_in ? lf.in_slots : stat_slots_of(p.n, block_n);
   p.ln_inv_k = lf.d_model > 0 ? 1.0f / (float)lf.d_model : 0.f;
   p.ln_eps = 1e-5f;
+  p.ln_guard = lf.stats_in ? lf.guard : nullptr;
+  p.ln_guard_min = 0.5f * kLnGuardLimit;
 }
 
 static int run_linear(const void* A, const void* W, void* C, const float* bias, const float* resid,
@@ -648,6 +655,14 @@ struct gww_model {
   std::vector<LayerDev> layers;
   std::vector<void*> owned;
   std::vector<void*> head_owned;   // device buffers of the current head (freed when the head is replaced)
+  // LayerNorm-fold guard (see kLnGuardLimit): device max of |mean|/std, its pinned host mirror, and the state machine
+  float* ln_guard_dev = nullptr;
+  float* ln_guard_host = nullptr;
+  cudaEvent_t ln_guard_ev = nullptr;
+  bool ln_guard_pending = false;
+  bool ln_fold_checked = false;    // the first folded chunk of this model has been verified synchronously
+  bool ln_fold_off = false;        // the guard tripped: this model runs the stand-alone LayerNorm kernel
+  float ln_ratio_seen = 0.f;
   bool has_head = false;
   HeadParams head{};
   float* head_scratch = nullptr;   // 2 x rows x kHeadMaxWidth ping-pong activations
@@ -785,11 +800,30 @@ extern "C" int gww_model_create(const gww_encoder_config_t* cfg, const gww_encod
     guard(dev_bf16(m, std::vector<float>(lw.fc2_w, lw.fc2_w + (size_t)d * f), &ld.fc2_w));
     guard(dev_f32(m, lw.fc2_b, d, &ld.fc2_b));
   }
+  if (rc == GWW_OK) {
+    if (cudaMalloc(&m->ln_guard_dev, sizeof(float)) != cudaSuccess || cudaMemset(m->ln_guard_dev, 0, sizeof(float)) != cudaSuccess ||
+        cudaMallocHost(&m->ln_guard_host, sizeof(float)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ln_guard_ev, cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(GWW_ERR_CUDA, "model_create: cannot allocate the LayerNorm-fold guard");
+    else
+      *m->ln_guard_host = 0.f;
+  }
   if (rc != GWW_OK) {
     gww_model_destroy(m);
     return rc;
   }
   *out = m;
+  return GWW_OK;
+}
+
+extern "C" int gww_model_ln_fold_state(const gww_model_t* m, float* max_ratio, int* fold_active) {
+  if (!m) return fail(GWW_ERR_INVALID, "ln_fold_state: null model");
+  float v = 0.f;
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpy(&v, m->ln_guard_dev, sizeof(float), cudaMemcpyDeviceToHost));
+  if (v < m->ln_ratio_seen) v = m->ln_ratio_seen;
+  if (max_ratio) *max_ratio = v;
+  if (fold_active) *fold_active = (m->ln_fold_off ? 0 : 1);
   return GWW_OK;
 }
 
@@ -833,6 +867,9 @@ extern "C" void gww_model_destroy(gww_model_t* m) {
   if (!m) return;
   for (void* p : m->owned) cudaFree(p);
   for (void* p : m->head_owned) cudaFree(p);
+  if (m->ln_guard_dev) cudaFree(m->ln_guard_dev);
+  if (m->ln_guard_host) cudaFreeHost(m->ln_guard_host);
+  if (m->ln_guard_ev) cudaEventDestroy(m->ln_guard_ev);
   if (m->head_scratch) cudaFree(m->head_scratch);
   delete m;
 }
@@ -898,19 +935,57 @@ static bool ln_fold_enabled() {
   return v != 0;
 }
 
-static int encoder_chunk(const gww_model* m, const Workspace& ws, int nc, float* last_hidden,
+static int encoder_chunk_impl(const gww_model* m, const Workspace& ws, int nc, float* last_hidden,
+                              float* pooled, int use_last_token, cudaStream_t stream, bool fold);
+
+// Runs one chunk; owns the LayerNorm-fold guard: the first folded chunk of a model is checked synchronously (and
+// redone with the stand-alone LayerNorm if the residual stream's |mean|/std exceeds kLnGuardLimit), later chunks are
+// checked without blocking (the running maximum comes back through pinned memory behind an event).
+static int encoder_chunk(const gww_model* cm, const Workspace& ws, int nc, float* last_hidden,
                          float* pooled, int use_last_token, cudaStream_t stream) {
+  gww_model* m = const_cast<gww_model*>(cm);
+  bool fold = ln_fold_enabled() && !m->ln_fold_off;
+  auto trip = [&](float ratio) {
+    m->ln_fold_off = true;
+    m->ln_ratio_seen = ratio;
+    fprintf(stderr, "gww: residual stream has |mean|/std = %.2f (> %.1f): LayerNorm folding disabled for this model, "
+                    "using the stand-alone LayerNorm kernel\n", ratio, kLnGuardLimit);
+  };
+  if (fold && m->ln_guard_pending && cudaEventQuery(m->ln_guard_ev) == cudaSuccess) {
+    m->ln_guard_pending = false;
+    if (*m->ln_guard_host > kLnGuardLimit) { trip(*m->ln_guard_host); fold = false; }
+  }
+  GWW_TRY(encoder_chunk_impl(m, ws, nc, last_hidden, pooled, use_last_token, stream, fold));
+  if (!fold) return GWW_OK;
+  if (!m->ln_fold_checked) {
+    float v = 0.f;
+    CU_TRY(cudaMemcpyAsync(&v, m->ln_guard_dev, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    m->ln_fold_checked = true;
+    if (v > kLnGuardLimit) {
+      trip(v);
+      return encoder_chunk_impl(m, ws, nc, last_hidden, pooled, use_last_token, stream, false);
+    }
+  } else if (!m->ln_guard_pending) {
+    CU_TRY(cudaMemcpyAsync(m->ln_guard_host, m->ln_guard_dev, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaEventRecord(m->ln_guard_ev, stream));
+    m->ln_guard_pending = true;
+  }
+  return GWW_OK;
+}
+
+static int encoder_chunk_impl(const gww_model* m, const Workspace& ws, int nc, float* last_hidden,
+                              float* pooled, int use_last_token, cudaStream_t stream, const bool fold) {
   const int d = m->cfg.d_model, f = m->cfg.ffn_dim;
   const long M = (long)nc * GWW_N_CTX;
   const int bn_d = pick_block_n(d), bn_3d = pick_block_n(3 * d), bn_f = pick_block_n(f);
   // out_proj (K = N = d) is HBM-bound (10 d bytes per row against 2 d^2 FLOP): a 128-wide N tile leaves room
   // for more operand stages in flight and measured 0.355 vs 0.449 ms (whisper-base, 384k rows; 5.5 TB/s)
   const int bn_o = (d % 128 == 0) ? 128 : bn_d;
-  const bool fold = ln_fold_enabled();
   // producer side of a residual GEMM / consumer side of the Linear after a LayerNorm
   auto produce = [&]() { LnFold lf; if (fold) { lf.xb = ws.xb; lf.stats_out = ws.stats; lf.d_model = d; } return lf; };
   auto consume = [&](const float* c1, int slots) {
-    LnFold lf; lf.stats_in = ws.stats; lf.c1 = c1; lf.in_slots = slots; lf.d_model = d; return lf;
+    LnFold lf; lf.stats_in = ws.stats; lf.c1 = c1; lf.in_slots = slots; lf.d_model = d; lf.guard = m->ln_guard_dev; return lf;
   };
   op16_t* h1 = ws.g;   // conv1 output [nc, 3001, d], row 0 of each sample = zero pad
   {  // zero pad row (t = -1) of every sample
@@ -1232,6 +1307,7 @@ struct gww_qfront {
   bool has_adapter = false;
   QAdapterDev ad{};
   int n_detectors = 0;
+  int c1 = 16, c2 = 32, c3 = 64;         // adapter CNN widths (inference.py:322-332; train.py:118-123 uses 32/64/128)
   std::vector<void*> owned;
 };
 
@@ -1257,9 +1333,9 @@ extern "C" int gww_qfront_create(double duration, double sample_rate, double qmi
   if (!out) return fail(GWW_ERR_INVALID, "qfront_create: null argument");
   if (duration * sample_rate != 2048.0)
     return fail(GWW_ERR_INVALID, "qfront_create: only duration*sample_rate == 2048 samples is supported");
-  if (!(qmin > 0 && qmax > qmin) || mismatch <= 0 || spec_t != 512 || spec_f < 16 || spec_f > 512 ||
-      (spec_f % 64) != 0)
-    return fail(GWW_ERR_INVALID, "qfront_create: unsupported parameters (spectrogram must be [64k<=512, 512])");
+  if (!(qmin > 0 && qmax > qmin) || mismatch <= 0 || spec_t < 64 || spec_t > 512 || (spec_t % 64) != 0 ||
+      spec_f < 64 || spec_f > 512 || (spec_f % 64) != 0)
+    return fail(GWW_ERR_INVALID, "qfront_create: unsupported parameters (spectrogram sides must be multiples of 64 in [64, 512])");
   const double PI = 3.14159265358979323846;
   gww_qfront* qf = new gww_qfront();
   qf->spec_f = spec_f; qf->spec_t = spec_t;
@@ -1397,22 +1473,28 @@ extern "C" int gww_qfront_set_adapter(gww_qfront_t* qf, const gww_qadapter_weigh
   if (w->n_detectors < 1 || w->n_detectors > 8)
     return fail(GWW_ERR_INVALID, "qfront_set_adapter: n_detectors=%d out of range", w->n_detectors);
   GWW_TRY(qf_ensure_device(qf));
-  std::vector<float> w1(9 * 16), b1(w->conv1_b, w->conv1_b + 16), w2(9 * 16 * 32), b2(w->conv2_b, w->conv2_b + 32),
-      w3(9 * 32 * 64), b3(w->conv3_b, w->conv3_b + 64), w4(w->conv4_w, w->conv4_w + 64);
-  for (int c = 0; c < 16; ++c)
-    for (int t = 0; t < 9; ++t) w1[t * 16 + c] = w->conv1_w[c * 9 + t];
-  for (int co = 0; co < 32; ++co)
-    for (int ci = 0; ci < 16; ++ci)
-      for (int t = 0; t < 9; ++t) w2[(t * 16 + ci) * 32 + co] = w->conv2_w[(co * 16 + ci) * 9 + t];
-  for (int co = 0; co < 64; ++co)
-    for (int ci = 0; ci < 32; ++ci)
-      for (int t = 0; t < 9; ++t) w3[(t * 32 + ci) * 64 + co] = w->conv3_w[(co * 32 + ci) * 9 + t];
+  const int C1 = w->c1 > 0 ? w->c1 : 16, C2 = w->c2 > 0 ? w->c2 : 32, C3 = w->c3 > 0 ? w->c3 : 64;
+  if (C1 % 16 || C2 % 16 || C3 % 16 || C1 > 64 || C2 > 128 || C3 > 256)
+    return fail(GWW_ERR_INVALID, "qfront_set_adapter: channel widths (%d, %d, %d) must be multiples of 16, <= (64, 128, 256)", C1, C2, C3);
+  qf->c1 = C1; qf->c2 = C2; qf->c3 = C3;
+  const bool std_geom = (C1 == 16 && C2 == 32 && C3 == 64);
+  std::vector<float> w1(9 * C1), b1(w->conv1_b, w->conv1_b + C1), w2((size_t)9 * C1 * C2), b2(w->conv2_b, w->conv2_b + C2),
+      w3((size_t)9 * C2 * C3), b3(w->conv3_b, w->conv3_b + C3), w4(w->conv4_w, w->conv4_w + C3);
+  for (int c = 0; c < C1; ++c)
+    for (int t = 0; t < 9; ++t) w1[t * C1 + c] = w->conv1_w[c * 9 + t];
+  for (int co = 0; co < C2; ++co)
+    for (int ci = 0; ci < C1; ++ci)
+      for (int t = 0; t < 9; ++t) w2[((size_t)t * C1 + ci) * C2 + co] = w->conv2_w[((size_t)co * C1 + ci) * 9 + t];
+  for (int co = 0; co < C3; ++co)
+    for (int ci = 0; ci < C2; ++ci)
+      for (int t = 0; t < 9; ++t) w3[((size_t)t * C2 + ci) * C3 + co] = w->conv3_w[((size_t)co * C2 + ci) * 9 + t];
   QAdapterDev ad{};
   GWW_TRY(qf_upload(qf, w1, &ad.w1)); GWW_TRY(qf_upload(qf, b1, &ad.b1));
   GWW_TRY(qf_upload(qf, w2, &ad.w2)); GWW_TRY(qf_upload(qf, b2, &ad.b2));
   GWW_TRY(qf_upload(qf, w3, &ad.w3)); GWW_TRY(qf_upload(qf, b3, &ad.b3));
   GWW_TRY(qf_upload(qf, w4, &ad.w4));
-  {  // bf16 hi/lo images of the conv2 / conv3 weights in the UMMA canonical layout (tensor-core path)
+  ad.w2p = nullptr; ad.w3p = nullptr;
+  if (std_geom) {  // bf16 hi/lo images of the conv2 / conv3 weights in the UMMA canonical layout (tensor-core path)
     uint4 *p2 = nullptr, *p3 = nullptr;
     CU_TRY(cudaMalloc(&p2, (size_t)QtCfg<16, 32>::kWBytes));
     qf->owned.push_back(p2);
@@ -1454,8 +1536,8 @@ static QWorkspace qcarve(const gww_qfront* qf, long n, uint8_t* base) {
   w.plane_max = (unsigned int*)take(64);
   w.plane_idx = (int*)take(64);
   w.spec = (float*)take(N * F * T * 4);
-  w.act1 = (float*)take(N * (F / 2) * (T / 2) * 16 * 4);
-  w.act2 = (float*)take(N * (F / 4) * (T / 4) * 32 * 4);
+  w.act1 = (float*)take(N * (F / 2) * (T / 2) * (size_t)qf->c1 * 4);
+  w.act2 = (float*)take(N * (F / 4) * (T / 4) * (size_t)qf->c2 * 4);
   w.map = (float*)take(N * (F / 4) * (T / 4) * 4);
   w.total = off;
   return w;
@@ -1508,7 +1590,24 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
   if (det < 0 || det >= qf->n_detectors) return fail(GWW_ERR_INVALID, "qadapter: det_idx=%d out of range", det);
   const int F = qf->spec_f, T = qf->spec_t;
   ProfScope ps(PK_QADAPTER, s);
-  if (qadapter_tc_enabled() && F % 64 == 0 && T % 32 == 0) {
+  const bool std_geom = (qf->c1 == 16 && qf->c2 == 32 && qf->c3 == 64);
+  if (!std_geom) {
+    // other adapter widths (MLGWSC-1/train.py geometry): generic fp32 kernels
+    const int C1 = qf->c1, C2 = qf->c2, C3 = qf->c3;
+    auto k1 = qadapter_conv_generic_kernel<true, false>;
+    auto k3 = qadapter_conv_generic_kernel<false, true>;
+    GWW_TRY(ensure_smem_attr(k1, 18 * 18 * 128 * 4));
+    GWW_TRY(ensure_smem_attr(k3, 18 * 18 * 128 * 4));
+    k1<<<dim3((T + 15) / 16, (F + 15) / 16, (unsigned)n), 256, (size_t)18 * 18 * 1 * 4, s>>>(spec, qf->ad.w1, qf->ad.b1, nullptr, 0.f,
+                                                                                         ws.act1, F, T, 1, C1);
+    LAUNCH_CHECK();
+    k1<<<dim3((T / 2 + 15) / 16, (F / 2 + 15) / 16, (unsigned)n), 256, (size_t)18 * 18 * C1 * 4, s>>>(ws.act1, qf->ad.w2, qf->ad.b2, nullptr,
+                                                                                                   0.f, ws.act2, F / 2, T / 2, C1, C2);
+    LAUNCH_CHECK();
+    k3<<<dim3((T / 4 + 15) / 16, (F / 4 + 15) / 16, (unsigned)n), 256, (size_t)18 * 18 * C2 * 4, s>>>(ws.act2, qf->ad.w3, qf->ad.b3, qf->ad.w4,
+                                                                                                   qf->ad.b4, ws.map, F / 4, T / 4, C2, C3);
+    LAUNCH_CHECK();
+  } else if (qadapter_tc_enabled() && F % 64 == 0 && T % 32 == 0) {
     // tensor-core path: conv1 (CUDA cores, fp32) writes bf16 hi/lo planes; conv2 / conv3 are tcgen05 implicit GEMMs
     qadapter_conv1_kernel<true><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
     LAUNCH_CHECK();

@@ -9,7 +9,7 @@
 // (B200 has full-rate-class FP64; the 1e-4 parity gate leaves no room for f32 leakage noise in the
 // out-of-band mel bins), one pass of coalesced 16-byte stores for the [80,3000] output.
 //
-// Algorithm (validated in numpy by tests/test_logmel_decomp.py):
+// Algorithm (validated in numpy by tests/test_oracle.py::test_kernel_decomposition_model):
 //   1. X = FFT_2048(x)                                   radix-2 Stockham in smem
 //   2. y[125q+r] = sum_k c_k e^{2 pi i k (125q+r)/16000}, |k|<=1024, c_k = X_k/2048 (c_+-1024 halved)
 //        k = 128a+k' :  E_r[k'] = sum_a C[a][k'] e^{2 pi i a r/125}
@@ -207,8 +207,12 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
           }
         }
         __syncwarp();
+        // twiddles by rotation in registers: t_k(n) = e^{2 pi i k n / 400} = t_k(n-1) * w_k.  (r1 fetched every
+        // t_k(n) from shared memory -- seven 16-byte loads per lane per n against 42 DFMA, and the twelve warps'
+        // loads, not the FP64 pipe, bound the kernel; the rotation costs 4 DFMA per bin instead and 199 steps of it
+        // lose ~2e-14, far below the 1e-4 gate.)
         double re[NF][7], im[NF][7];
-        int jj[7];
+        double tc[7], ts[7], wc[7], wsn[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
           const int k = lane + 32 * i;
@@ -217,7 +221,10 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
             re[ff][i] = (k & 1) ? -u200[ff] : u200[ff];
             im[ff][i] = 0.0;
           }
-          jj[i] = 0;
+          const int kk = (k < 400) ? k : 0;
+          const double2 w1 = tw400[kk + (kk >> 3)];
+          wc[i] = w1.x; wsn[i] = w1.y;
+          tc[i] = 1.0; ts[i] = 0.0;
         }
 #pragma unroll 1
         for (int nn = 1; nn < 200; ++nn) {
@@ -231,15 +238,13 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
           }
 #pragma unroll
           for (int i = 0; i < 7; ++i) {
-            const int k = lane + 32 * i;
-            int j = jj[i] + k;
-            if (j >= 400) j -= 400;
-            jj[i] = j;
-            const double2 t = tw400[j + (j >> 3)];
+            const double c2 = fma(tc[i], wc[i], -(ts[i] * wsn[i]));
+            ts[i] = fma(ts[i], wc[i], tc[i] * wsn[i]);
+            tc[i] = c2;
 #pragma unroll
             for (int ff = 0; ff < NF; ++ff) {
-              re[ff][i] = fma(ev[ff], t.x, re[ff][i]);
-              im[ff][i] = fma(ov[ff], t.y, im[ff][i]);
+              re[ff][i] = fma(ev[ff], tc[i], re[ff][i]);
+              im[ff][i] = fma(ov[ff], ts[i], im[ff][i]);
             }
           }
         }

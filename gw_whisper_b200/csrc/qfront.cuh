@@ -690,6 +690,78 @@ qadapter_conv3_kernel(const float* __restrict__ act2, float* __restrict__ map, i
   }
 }
 
+// Generic 3x3 convolution (pad 1) + ReLU for adapter geometries other than the inference default (e.g. the
+// 128x128 / 32-64-128 adapter of MLGWSC-1/train.py:104,118-123): NHWC fp32 in, weights [9][CI][CO], any CI and
+// any CO that is a multiple of 16.  CTA = 16x16 conv pixels, thread = one pixel, 16 output channels at a time.
+//   POOL : + maxpool2 -> out NHWC [n, H/2, W/2, CO]
+//   FINAL: + conv1x1(CO -> 1) + b4 -> out map [n, H, W]
+// Correctness path (fp32 CUDA cores, ~10 TFLOP/s); the default geometry runs on the tensor cores (qadapter_tc.cuh).
+template <bool POOL, bool FINAL>
+__global__ void __launch_bounds__(256)
+qadapter_conv_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
+                             const float* __restrict__ w4, float b4, float* __restrict__ out, int H, int W, int CI, int CO) {
+  extern __shared__ __align__(16) float cg_tile[];          // [18][18][CI]
+  const long n = blockIdx.z;
+  const int y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
+  const float* src = in + n * static_cast<long>(H) * W * CI;
+  for (int i = threadIdx.x; i < 18 * 18 * CI; i += 256) {
+    const int pix = i / CI, c = i - pix * CI;
+    const int y = y0 - 1 + pix / 18, x = x0 - 1 + pix % 18;
+    cg_tile[i] = (y >= 0 && y < H && x >= 0 && x < W) ? src[(static_cast<long>(y) * W + x) * CI + c] : 0.f;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int y = y0 + ty, x = x0 + tx;
+  float fin = b4;
+  for (int c0 = 0; c0 < CO; c0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = __ldg(b + c0 + c);
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* t = cg_tile + ((ty + tap / 3) * 18 + tx + tap % 3) * CI;
+      const float4* wp = reinterpret_cast<const float4*>(w + (static_cast<long>(tap) * CI) * CO + c0);
+      for (int ci = 0; ci < CI; ++ci) {
+        const float v = t[ci];
+        const float4* wr = wp + static_cast<long>(ci) * (CO / 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = __ldg(wr + q);
+          acc[4 * q] = fmaf(v, ww.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+        }
+      }
+    }
+    if constexpr (FINAL) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) fin = fmaf(fmaxf(acc[c], 0.f), __ldg(w4 + c0 + c), fin);
+    } else if constexpr (POOL) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float v = fmaxf(acc[c], 0.f);
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));     // x partner
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));    // y partner (a warp holds two tile rows)
+        acc[c] = v;
+      }
+      if (((tx | ty) & 1) == 0 && y < H && x < W) {
+        float* dst = out + ((n * (H >> 1) + (y >> 1)) * static_cast<long>(W >> 1) + (x >> 1)) * CO + c0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dst[c] = acc[c];
+      }
+    } else {
+      if (y < H && x < W) {
+        float* dst = out + ((n * H + y) * static_cast<long>(W) + x) * CO + c0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dst[c] = fmaxf(acc[c], 0.f);
+      }
+    }
+  }
+  if constexpr (FINAL) {
+    if (y < H && x < W) out[(n * H + y) * static_cast<long>(W) + x] = fin;
+  }
+}
+
 // AdaptiveAvgPool2d((OF, OT)) of map [n,H,W] + scale/bias + FiLM(det) -> feats.
 //   out_f32: [n, OF, OT] (reference layout) or nullptr
 //   out_tm : bf16 time-major, det-window w at out_tm + (w*tm_stride_w + tm_off) * (OT+2)*OF, with zero

@@ -15,7 +15,24 @@ from .encoder import B200WhisperEncoder
 
 
 def _linears(seq: nn.Sequential):
-    return [(m.weight, m.bias) for m in seq if isinstance(m, nn.Linear)]
+    return [(m.weight, m.bias if m.bias is not None else torch.zeros(m.out_features)) for m in seq
+            if isinstance(m, nn.Linear)]
+
+
+def replace_softmax_by_mutual_subtraction(network) -> None:
+    """Efficiency_test's "unbounded softmax replacement" (Signal_vs_Noise/Efficiency_test/src/test_network.py:89-99):
+    the trailing nn.Softmax of the 2-class head is replaced by a fixed bias-free Linear(2, 2) with weight
+    [[1, -1], [-1, 1]], i.e. the outputs become (x0 - x1, x1 - x0).  Raises ValueError like the reference when the
+    last layer is not a Softmax."""
+    layers = list(network.classifier.children())
+    if not isinstance(layers[-1], nn.Softmax):
+        raise ValueError("The last layer of the classifier is not a Softmax layer.")
+    new_layer = nn.Linear(2, 2, bias=False)
+    new_layer.weight = nn.Parameter(torch.tensor([[1.0, -1.0], [-1.0, 1.0]]), requires_grad=False)
+    layers[-1] = new_layer
+    network.classifier = nn.Sequential(*layers)
+    if hasattr(network, "refresh"):
+        network.refresh()
 
 
 class _B200Classifier(nn.Module):

@@ -103,16 +103,18 @@ class QTransformAdapter(nn.Module):
 
     def __init__(self, kernel_length: float = 1.0, sample_rate: int = 2048, q_range: Sequence[int] = (4, 128),
                  spectrogram_shape: Sequence[int] = (512, 512), target_shape: Tuple[int, int] = (80, 3000),
-                 n_detectors: int = 2) -> None:
+                 n_detectors: int = 2, channels: Sequence[int] = (16, 32, 64)) -> None:
         super().__init__()
         if tuple(target_shape) != (80, 3000):
             raise ValueError("the Whisper encoder needs target_shape == (80, 3000)")
         self.n_detectors = n_detectors
+        self.channels = tuple(int(c) for c in channels)
+        c1, c2, c3 = self.channels
         object.__setattr__(self, "q_transform", QScanB200(kernel_length, sample_rate, spectrogram_shape, q_range))
         self.freq_adapter = nn.Sequential(
-            nn.Conv2d(1, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
-            nn.Conv2d(16, 32, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
-            nn.Conv2d(32, 64, 3, padding=1), nn.ReLU(), nn.Conv2d(64, 1, 1))
+            nn.Conv2d(1, c1, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+            nn.Conv2d(c1, c2, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+            nn.Conv2d(c2, c3, 3, padding=1), nn.ReLU(), nn.Conv2d(c3, 1, 1))
         self.final_pool = nn.AdaptiveAvgPool2d(target_shape)
         self.scale = nn.Parameter(torch.ones(1))
         self.bias = nn.Parameter(torch.zeros(1))
@@ -141,8 +143,10 @@ class QTransformAdapter(nn.Module):
         w.scale, w.bias = float(self.scale.item()), float(self.bias.item())
         w.n_detectors = int(self.n_detectors)
         w.film_gamma, w.film_beta = _p(arrs[8]), _p(arrs[9])
+        w.c1, w.c2, w.c3 = self.channels
         qt = self.q_transform
         _lib.check(qt._lib.gww_qfront_set_adapter(qt._h, C.byref(w)))
+        qt._ws, qt._ws_n = None, 0       # the activation buffers are sized by the CNN widths: re-query
         self._dirty = False
 
     @torch.no_grad()
@@ -160,8 +164,21 @@ class QTransformAdapter(nn.Module):
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, D, _ = x.shape
+        self._sync()
         outs = [self.adapt(self.q_transform(x[:, i]), i) for i in range(D)]
         return torch.stack(outs, dim=1)
+
+
+class TrainQTransformAdapter(QTransformAdapter):
+    """The adapter geometry MLGWSC-1/train.py trains (`QTransformAdapter` there, :78-160): a 128x128 Q-spectrogram
+    (:104) and a 32 / 64 / 128 CNN (:118-123); same parameter names, so its checkpoints
+    (`save_model_components`, train.py:723) load here.  Runs on the generic fp32 convolution kernels."""
+
+    def __init__(self, kernel_length: float = 1.0, sample_rate: int = 2048, q_range: Sequence[int] = (4, 128),
+                 spectrogram_shape: Sequence[int] = (128, 128), target_shape: Tuple[int, int] = (80, 3000),
+                 n_detectors: int = 2) -> None:
+        super().__init__(kernel_length, sample_rate, q_range, spectrogram_shape, target_shape, n_detectors,
+                         channels=(32, 64, 128))
 
 
 class GWWhisperClassifier(nn.Module):

@@ -108,6 +108,12 @@ int gww_model_create(const gww_encoder_config_t* cfg, const gww_encoder_weights_
                      gww_model_t** out);
 int gww_model_set_head(gww_model_t* m, const gww_head_weights_t* head);
 void gww_model_destroy(gww_model_t* m);
+/* LayerNorm folding (the LayerNorms are evaluated inside the neighbouring GEMMs on the raw residual stream) loses
+ * precision when residual rows have a large common mode.  The library watches max |mean|/std over the rows it
+ * normalises and switches a model to the stand-alone LayerNorm kernel when it exceeds 4 (fp16 operands; 1.5 for
+ * bf16): the first chunk is checked synchronously and recomputed if needed, later ones asynchronously.  This call
+ * (synchronising) reports the maximum seen and whether folding is still active.  GWW_LN_FOLD=0 disables folding. */
+int gww_model_ln_fold_state(const gww_model_t* m, float* max_ratio, int* fold_active);
 /* Device bytes needed by forward calls that process up to `chunk` det-windows at a time. */
 size_t gww_workspace_bytes(const gww_model_t* m, int chunk);
 
@@ -165,7 +171,8 @@ int gww_threshold_compact(const float* out, int C, long n, float thr, long idx_b
 /* ---- front end B: Q-transform + Q-Adapter (MLGWSC-1) --------------------------------------------- */
 /* Replaces QTransformAdapter (MLGWSC-1/inference.py:303-351) including ml4gw.transforms.QScan
  * (:316-321, :345).  The handle holds the (q, f) tiling plan, bisquare windows and, once set, the
- * adapter CNN weights.  Only duration * sample_rate == 2048 is supported (1 s @ 2048 Hz). */
+ * adapter CNN weights.  Only duration * sample_rate == 2048 is supported (1 s @ 2048 Hz); the spectrogram sides
+ * are multiples of 64 in [64, 512] ([512,512] at inference.py:310, [128,128] at train.py:104). */
 typedef struct gww_qfront gww_qfront_t;
 
 typedef struct {
@@ -176,6 +183,9 @@ typedef struct {
   float scale, bias;                /* QTransformAdapter.scale / .bias (inference.py:334-335) */
   int n_detectors;                  /* <= 8 */
   const float *film_gamma, *film_beta; /* host [n_detectors] (:336-337) */
+  int c1, c2, c3;                   /* CNN widths; 0 = the inference defaults 16 / 32 / 64.  MLGWSC-1/train.py:118-123
+                                     * trains a 32 / 64 / 128 adapter on a 128x128 Q-spectrogram (:104): conv weights
+                                     * are then [c1,1,3,3], [c2,c1,3,3], [c3,c2,3,3], [1,c3,1,1] */
 } gww_qadapter_weights_t;
 
 int gww_qfront_create(double duration, double sample_rate, double qmin, double qmax, double mismatch,

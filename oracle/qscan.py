@@ -183,15 +183,17 @@ class QTransformAdapter(nn.Module):
 
     def __init__(self, kernel_length: float = 1.0, sample_rate: int = 2048, q_range: Sequence[int] = (4, 128),
                  spectrogram_shape: Sequence[int] = (512, 512), target_shape: Tuple[int, int] = (80, 3000),
-                 n_detectors: int = 2):
+                 n_detectors: int = 2, channels: Sequence[int] = (16, 32, 64)):
+        # channels=(32, 64, 128) with spectrogram_shape=(128, 128) is the adapter of MLGWSC-1/train.py:104,118-123
         super().__init__()
         self.n_detectors = n_detectors
+        c1, c2, c3 = channels
         self.q_transform = QScan(duration=kernel_length, sample_rate=sample_rate,
                                  spectrogram_shape=list(spectrogram_shape), qrange=list(q_range))
         self.freq_adapter = nn.Sequential(
-            nn.Conv2d(1, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
-            nn.Conv2d(16, 32, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
-            nn.Conv2d(32, 64, 3, padding=1), nn.ReLU(), nn.Conv2d(64, 1, 1))
+            nn.Conv2d(1, c1, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+            nn.Conv2d(c1, c2, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+            nn.Conv2d(c2, c3, 3, padding=1), nn.ReLU(), nn.Conv2d(c3, 1, 1))
         self.final_pool = nn.AdaptiveAvgPool2d(target_shape)
         self.scale = nn.Parameter(torch.ones(1))
         self.bias = nn.Parameter(torch.zeros(1))

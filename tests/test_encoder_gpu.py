@@ -95,6 +95,44 @@ def test_last_token_pruning_matches_full_final_layer():
     assert e_pf < HID_TOL and e_p < HID_TOL and e_f < HID_TOL
 
 
+def test_layernorm_fold_guard_switches_on_a_large_common_mode():
+    """the folded LayerNorm (var = E[x^2] - mean^2 on 16-bit copies of x) is only safe while
+    |mean|/std of the residual rows is small.  A checkpoint with a large common-mode residual (here: +40 added to
+    every positional embedding) must trip the runtime guard on its first chunk, be recomputed with the stand-alone
+    LayerNorm kernel, and still match the fp32 oracle."""
+    import ctypes as C
+    from oracle import encoder as E, logmel as L
+    from gw_whisper_b200 import B200WhisperEncoder, _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    feats = torch.from_numpy(L.logmel_restated(_strain(4)[:, 0].numpy())).to(dev)
+
+    def state(enc):
+        r, a = C.c_float(), C.c_int()
+        _lib.check(lib.gww_model_ln_fold_state(enc._handle, C.byref(r), C.byref(a)))
+        return r.value, a.value
+
+    base = E.make_encoder("tiny", 0, spread=True)
+    ok = B200WhisperEncoder.from_hf(base, chunk=4)
+    ok.pooled(feats)
+    r_ok, active_ok = state(ok)
+    print(f"regular weights: max |mean|/std = {r_ok:.2f}, fold active = {active_ok}")
+    assert active_ok == 1 and r_ok < 4.0
+    with torch.no_grad():
+        base.embed_positions.weight += 40.0
+    with torch.no_grad():
+        ref = base.to(dev)(feats).last_hidden_state[:, -1, :].cpu()
+    enc = B200WhisperEncoder.from_hf(base.cpu(), chunk=4)
+    got = enc.pooled(feats).cpu()
+    r, active = state(enc)
+    e = (got - ref).abs().max().item()
+    print(f"common-mode weights: max |mean|/std = {r:.1f}, fold active = {active}, pooled err vs fp32 oracle {e:.3e}")
+    assert active == 0 and r > 4.0
+    assert e < HID_TOL
+    got2 = enc.pooled(feats).cpu()                     # stays on the stand-alone LayerNorm path
+    assert torch.equal(got, got2)
+
+
 def test_encoder_rejects_bad_length():
     from oracle import encoder as E
     from gw_whisper_b200 import B200WhisperEncoder
