@@ -31,7 +31,10 @@ def test_unsupported_geometry_is_rejected():
     with pytest.raises(RuntimeError):
         QScanB200(2.0, 2048, [512, 512], [4, 128])            # 4096 samples: not this path
     with pytest.raises(RuntimeError):
-        QScanB200(1.0, 2048, [512, 256], [4, 128])
+        QScanB200(1.0, 2048, [512, 250], [4, 128])            # sides must be multiples of 64 in [64, 512]
+    with pytest.raises(RuntimeError):
+        QScanB200(1.0, 2048, [1024, 512], [4, 128])
+    QScanB200(1.0, 2048, [128, 128], [4, 128])                # the MLGWSC-1/train.py geometry is supported
 
 
 def test_adapter_state_dict_keys_match_reference_and_qtransform_buffers_are_ignored():
