@@ -270,12 +270,29 @@ def mlgwsc_record(args, dev, rank, world, lib):
         if os.path.exists(pk_path):
             hbm_peak = float(json.load(open(pk_path)).get("hbm_gbs", hbm_peak))
         n_dw0 = 2 * sum(p.n_windows for p in plan[0])      # det-windows rank 0 processed in the profiled pass
+        # front-end kernels of rank 0's shard against the roofline that bounds each (algorithmic work per det-window,
+        # QScan 8 KB in + 1 MB spectrogram out; conv1 1 MB in + 4 MB of bf16 hi/lo planes out; conv2 /
+        # conv3 604 MFLOP each -- counted once, although the split-precision path executes three MMAs per product;
+        # pool 64 KB in + 480 KB of time-major features out)
+        peak_tf = 1590.0
+        if os.path.exists(pk_path):
+            pk = json.load(open(pk_path))
+            peak_tf = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", peak_tf)))
+        spec_fe = {"qscan": ("hbm", 2048 * 4 + 512 * 512 * 4), "qadapter_conv1": ("hbm", 512 * 512 * 4 + 256 * 256 * 64),
+                   "qadapter_conv2": ("tensor", 2.0 * 256 * 256 * 9 * 16 * 32), "qadapter_conv3": ("tensor", 2.0 * 128 * 128 * 9 * 32 * 64),
+                   "qadapter_pool": ("hbm", 128 * 128 * 4 + 3002 * 80 * 2), "qadapter": ("hbm", 512 * 512 * 4 + 3002 * 80 * 2)}
         fe = {}
-        for nm, bytes_per_dw in (("qscan", 2048 * 4 + 512 * 512 * 4), ("qadapter", 512 * 512 * 4 + 3002 * 80 * 2)):
-            if nm in kernels:
-                gbs = bytes_per_dw * n_dw0 / (kernels[nm]["ms"] * 1e-3) / 1e9
-                fe[nm] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                          "algorithmic_bytes_per_det_window": bytes_per_dw, "ms": kernels[nm]["ms"], "traffic": None}
+        for nm, (bound, work) in spec_fe.items():
+            if nm not in kernels:
+                continue
+            rate = work * n_dw0 / (kernels[nm]["ms"] * 1e-3)
+            if bound == "hbm":
+                fe[nm] = {"bound": "hbm", "achieved": rate / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": rate / 1e9 / hbm_peak,
+                          "algorithmic_bytes_per_det_window": work, "ms": kernels[nm]["ms"], "traffic": None}
+            else:
+                fe[nm] = {"bound": "tensor", "achieved": rate / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                          "frac": rate / 1e12 / peak_tf, "algorithmic_flops_per_det_window": work, "ms": kernels[nm]["ms"],
+                          "traffic": None, "note": "bf16 hi/lo split precision: 3 MMAs per algorithmic product"}
         dom = max(fe, key=lambda k: fe[k]["ms"]) if fe else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -40,7 +40,7 @@ constexpr int kApStages = GWW_AP_STAGES;   // K/V ring depth (each stage = one 1
 // kApGroup * kApLookahead MUFUs of a warp are queued at a time: the MIO queue of the sub-partition, which
 // the MMA / TMA warps' mbarrier instructions also go through, is not permanently full of MUFUs.  0 = off.
 #ifndef GWW_AP_GROUP
-#define GWW_AP_GROUP 4
+#define GWW_AP_GROUP 16    // r2 sweep with the polynomial share below (profiles/r2_attn_tune.jsonl): 4 -> 16
 #endif
 #ifndef GWW_AP_LOOKAHEAD
 #define GWW_AP_LOOKAHEAD 2
@@ -53,8 +53,10 @@ constexpr int kApLookahead = GWW_AP_LOOKAHEAD;
 // Of every 8 consecutive pairs of scores, GWW_AP_POLY pairs take their exponentials from the FMA pipe
 // (poly_exp2_pair) instead of MUFU.EX2: the kernel is bound by the XU pipe (MUFU.EX2 16 / clk / SM, r1 ncu: XU 68 %,
 // tensor 34 %), the fp32 pipe has slack.  Not used in the masked last key tile (-inf scores).  0 = all MUFU.
+// r2 sweep, 256 det-windows of whisper-base, ms per launch: (poly, group, lookahead) = (0,4,2) 1.654 [round 1],
+// (0,0,2) 1.625, (2,0,2) 1.625, (2,8,2) 1.566, (2,16,2) 1.562, (3,0,2) 1.572, (4,0,2) 1.707, (4,8,3) 1.673.
 #ifndef GWW_AP_POLY
-#define GWW_AP_POLY 0
+#define GWW_AP_POLY 2
 #endif
 #ifndef GWW_ATTN_POLL_NS
 #define GWW_ATTN_POLL_NS 64   // back-off of the MMA warp's polling loop when nothing is ready

@@ -113,12 +113,14 @@ static int ensure_smem_attr(K kern, int bytes) {
 // ------------------------------------------------------------------------------------------------
 enum ProfKind : int {
   PK_LOGMEL = 0, PK_FEATS_TM, PK_GEMM_CONV1, PK_GEMM_CONV2, PK_LN, PK_GEMM_QKV, PK_ATTN, PK_GEMM_O,
-  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_ATTN_LAST, PK_WHITEN, PK_COUNT
+  PK_GEMM_FC1, PK_GEMM_FC2, PK_HEAD, PK_OTHER, PK_QSCAN, PK_QADAPTER, PK_ATTN_LAST, PK_WHITEN, PK_QA_CONV1, PK_QA_CONV2,
+  PK_QA_CONV3, PK_QA_POOL, PK_COUNT
 };
 static const char* kProfNames[PK_COUNT] = {"logmel", "feats_to_timemajor", "gemm_conv1", "gemm_conv2",
                                            "layernorm", "gemm_qkv", "attention", "gemm_out_proj",
                                            "gemm_fc1", "gemm_fc2", "head", "other", "qscan", "qadapter",
-                                           "attention_last_row", "whiten"};
+                                           "attention_last_row", "whiten", "qadapter_conv1", "qadapter_conv2",
+                                           "qadapter_conv3", "qadapter_pool"};
 struct ProfRec { cudaEvent_t a, b; int kind; };
 // The profiler is a single-device, single-thread diagnostic (bench.py): records are kept in a deque so that
 // pointers stay valid while it grows, the bookkeeping is under g_prof_mu, and records made on another device
@@ -1589,10 +1591,10 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
   if (!qf->has_adapter) return fail(GWW_ERR_INVALID, "qadapter: no adapter weights set");
   if (det < 0 || det >= qf->n_detectors) return fail(GWW_ERR_INVALID, "qadapter: det_idx=%d out of range", det);
   const int F = qf->spec_f, T = qf->spec_t;
-  ProfScope ps(PK_QADAPTER, s);
   const bool std_geom = (qf->c1 == 16 && qf->c2 == 32 && qf->c3 == 64);
   if (!std_geom) {
     // other adapter widths (MLGWSC-1/train.py geometry): generic fp32 kernels
+    ProfScope ps(PK_QADAPTER, s);
     const int C1 = qf->c1, C2 = qf->c2, C3 = qf->c3;
     auto k1 = qadapter_conv_generic_kernel<true, false>;
     auto k3 = qadapter_conv_generic_kernel<false, true>;
@@ -1609,7 +1611,10 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
     LAUNCH_CHECK();
   } else if (qadapter_tc_enabled() && F % 64 == 0 && T % 32 == 0) {
     // tensor-core path: conv1 (CUDA cores, fp32) writes bf16 hi/lo planes; conv2 / conv3 are tcgen05 implicit GEMMs
-    qadapter_conv1_kernel<true><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
+    {
+      ProfScope ps(PK_QA_CONV1, s);
+      qadapter_conv1_kernel<true><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
+    }
     LAUNCH_CHECK();
     using C2 = QtCfg<16, 32>;
     using C3 = QtCfg<32, 64>;
@@ -1621,13 +1626,20 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
     const int sms = g_num_sms;
     const int grid2 = (int)std::min<long>(sms, (tiles2 + C2::kGroups - 1) / C2::kGroups);
     const int grid3 = (int)std::min<long>(sms, (tiles3 + C3::kGroups - 1) / C3::kGroups);
-    k2<<<grid2, C2::kThreads, C2::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act1), qf->ad.w2p, qf->ad.b2, nullptr, 0.f,
-                                                  ws.act2, F / 2, T / 2, n);
+    {
+      ProfScope ps(PK_QA_CONV2, s);
+      k2<<<grid2, C2::kThreads, C2::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act1), qf->ad.w2p, qf->ad.b2, nullptr, 0.f,
+                                                    ws.act2, F / 2, T / 2, n);
+    }
     LAUNCH_CHECK();
-    k3<<<grid3, C3::kThreads, C3::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act2), qf->ad.w3p, qf->ad.b3, qf->ad.w4,
-                                                  qf->ad.b4, ws.map, F / 4, T / 4, n);
+    {
+      ProfScope ps(PK_QA_CONV3, s);
+      k3<<<grid3, C3::kThreads, C3::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act2), qf->ad.w3p, qf->ad.b3, qf->ad.w4,
+                                                    qf->ad.b4, ws.map, F / 4, T / 4, n);
+    }
     LAUNCH_CHECK();
   } else {
+    ProfScope ps(PK_QADAPTER, s);
     qadapter_conv1_kernel<false><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
     LAUNCH_CHECK();
     qadapter_conv2_kernel<<<dim3(T / 32, F / 32, (unsigned)n), 256, kC2SmemBytes, s>>>(ws.act1, ws.act2, F / 2, T / 2, qf->ad);
@@ -1635,8 +1647,11 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
     qadapter_conv3_kernel<<<dim3(T / 64, F / 64, (unsigned)n), 256, kC3SmemBytes, s>>>(ws.act2, ws.map, F / 4, T / 4, qf->ad);
     LAUNCH_CHECK();
   }
-  qadapter_pool_kernel<<<dim3((GWW_N_FRAMES + 127) / 128, (unsigned)n), 256, 0, s>>>(
-      ws.map, feats_f32, feats_tm, tm_stride_w, tm_off, F / 4, T / 4, GWW_N_MELS, GWW_N_FRAMES, det, qf->ad);
+  {
+    ProfScope ps(PK_QA_POOL, s);
+    qadapter_pool_kernel<<<dim3((GWW_N_FRAMES + 127) / 128, (unsigned)n), 256, 0, s>>>(
+        ws.map, feats_f32, feats_tm, tm_stride_w, tm_off, F / 4, T / 4, GWW_N_MELS, GWW_N_FRAMES, det, qf->ad);
+  }
   LAUNCH_CHECK();
   return GWW_OK;
 }

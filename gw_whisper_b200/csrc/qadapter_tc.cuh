@@ -18,10 +18,10 @@
 //     a tap (dy, dx) is nothing but the descriptor's start address moved by (dy*10 + dx) x 16 B.  Nine taps =
 //     nine descriptors into the same staged tile; zero padding comes from the staging loads.
 //   * weights live in shared memory in the same canonical layout ([tap][plane][Cout] x 16 B, hi and lo).
-//   * one persistent CTA per SM made of G independent 128-thread groups (named barriers): each group loops
-//     stage tile -> 27 / 54 MMAs issued by one elected thread -> tcgen05.commit -> tcgen05.ld -> epilogue, and
-//     the groups interleave on the tensor pipe; the next tile is staged before the epilogue math of the current
-//     one.  Activations move between the kernels in the plane format (bf16 hi/lo): act1 4 planes of 256x256,
+//   * one persistent CTA per SM made of G independent 128-thread groups (named barriers): each group runs a
+//     software pipeline over its tiles with two staging buffers -- cp.async of tile t+2 in flight, tile t+1 resident,
+//     27 / 54 MMAs of tile t issued by one elected thread -> tcgen05.commit -> tcgen05.ld -> epilogue of tile t
+//     overlapping the MMAs of tile t+1 -- and the groups interleave on the tensor pipe.  Activations move between the kernels in the plane format (bf16 hi/lo): act1 4 planes of 256x256,
 //     act2 8 planes of 128x128 -- the same bytes as the fp32 NHWC tensors of round 1.
 //   * epilogues: conv2 = 2x2 max-pool by warp shuffles (the 16x8 tile maps pool partners to lanes ^1 and ^8),
 //     bias, ReLU, hi/lo split, 16-byte plane stores; conv3 = bias, ReLU, the 1x1 conv (64 -> 1) as a dot product.
@@ -43,10 +43,11 @@ struct QtCfg {
   static constexpr int kTileBytes = kPlanes * kQtPlaneBytes;
   static constexpr int kWElems = 9 * kPlanes * COUT;     // 16-byte weight elements
   static constexpr int kWBytes = kWElems * 16;
-  static constexpr int kGroups = (CIN == 16) ? 6 : 4;     // register file: 768 x 85 / 512 x 128 registers
+  static constexpr int kGroups = (CIN == 16) ? 6 : 3;     // shared memory (two staging buffers per group) and registers
+  static constexpr int kBufs = 2;                         // staging buffers per group: tile t+2 loads while t+1 computes
   static constexpr int kThreads = kGroups * kQtGroupThreads;
   static constexpr int kTmemCols = (kGroups * COUT <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kWBytes + kGroups * kTileBytes + COUT * 8 + 64 + kGroups * 8 + 16;
+  static constexpr int kSmemBytes = kWBytes + kGroups * kBufs * kTileBytes + COUT * 8 + 64 + kGroups * 8 + 16;
 };
 
 // no-swizzle K-major shared-memory matrix descriptor (see header comment)
@@ -68,6 +69,7 @@ __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const void*
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
@@ -113,7 +115,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   extern __shared__ __align__(128) uint8_t qt_smem[];
   uint4* w_s = reinterpret_cast<uint4*>(qt_smem);
   uint8_t* tiles = qt_smem + Cfg::kWBytes;
-  float* bias_s = reinterpret_cast<float*>(tiles + Cfg::kGroups * Cfg::kTileBytes);
+  float* bias_s = reinterpret_cast<float*>(tiles + Cfg::kGroups * Cfg::kBufs * Cfg::kTileBytes);
   float* w4_s = bias_s + COUT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w4_s + COUT + 16);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::kGroups);
@@ -141,8 +143,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(grp * COUT);   // this group's accumulator columns
   const uint32_t bar = smem_u32(&bars[grp]);
-  uint4* tile = reinterpret_cast<uint4*>(tiles + grp * Cfg::kTileBytes);
-  const uint32_t tile_addr = smem_u32(tile);
+  const uint32_t tile_addr0 = smem_u32(tiles + grp * Cfg::kBufs * Cfg::kTileBytes);   // buffer b at + b * kTileBytes
   const uint32_t w_addr = smem_u32(w_s);
 
   const int tiles_x = W / kQtTileW, tiles_y = H / kQtTileH;
@@ -150,7 +151,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   const long n_tiles = tiles_per_img * n_img;
   const long stride = static_cast<long>(gridDim.x) * Cfg::kGroups;
   constexpr uint32_t kIdesc = make_idesc_bf16(128, COUT);
-  auto issue_mmas = [&]() {
+  auto issue_mmas = [&](const uint32_t tile_addr) {
     // three split terms: (A hi, W hi), (A lo, W hi), (A hi, W lo); per tap, per pair of 8-channel chunks (K = 16)
     uint32_t first = 1;
 #pragma unroll 1
@@ -171,7 +172,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
     }
   };
   // stage the haloed tile of tile index t: 16-byte cp.async per element, zero-filled outside the image
-  auto stage_tile = [&](long t) {
+  auto stage_tile = [&](long t, const uint32_t tile_addr) {
     const long img = t / tiles_per_img;
     const int rem = static_cast<int>(t - img * tiles_per_img);
     const int ty0 = (rem / tiles_x) * kQtTileH - 1, tx0 = (rem % tiles_x) * kQtTileW - 1;
@@ -185,29 +186,39 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
     }
     cp_async_commit();
   };
-  auto publish_and_issue = [&]() {
-    cp_async_wait_all();
+  // tile staged by all 128 threads of the group + accumulator drained by its four warps -> one thread issues the MMAs
+  auto publish_and_issue = [&](const uint32_t tile_addr) {
     fence_proxy_async_smem();
-    named_bar_sync(1 + grp, kQtGroupThreads);            // tile staged by all 128 threads, accumulator drained
+    named_bar_sync(1 + grp, kQtGroupThreads);
     if (wig == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_mmas();
+        issue_mmas(tile_addr);
         umma_commit(bar);
       }
       __syncwarp();
     }
   };
 
+  // Software pipeline per group (two staging buffers): while the MMAs of tile t run, tile t+1 is already resident and
+  // tile t+2 is in flight (cp.async); the epilogue of tile t overlaps the MMAs of tile t+1.
   long t = static_cast<long>(blockIdx.x) * Cfg::kGroups + grp;
   uint32_t phase = 0;
+  int it = 0;
   if (t < n_tiles) {
-    stage_tile(t);
-    publish_and_issue();
+    stage_tile(t, tile_addr0);
+    if (t + stride < n_tiles) {
+      stage_tile(t + stride, tile_addr0 + Cfg::kTileBytes);
+      cp_async_wait_1();
+    } else {
+      cp_async_wait_all();
+    }
+    publish_and_issue(tile_addr0);
   }
   while (t < n_tiles) {
-    const long tn = t + stride;
-    mbar_wait(bar, phase);                               // MMAs of tile t done: accumulator ready, staging buffer free
+    const long tn = t + stride, tnn = tn + stride;
+    const uint32_t buf_t = tile_addr0 + (it & 1) * Cfg::kTileBytes, buf_n = tile_addr0 + ((it + 1) & 1) * Cfg::kTileBytes;
+    mbar_wait(bar, phase);                               // MMAs of tile t done: accumulator ready, buffer of t free
     phase ^= 1;
     tc_fence_after();
     uint32_t acc[COUT];
@@ -216,7 +227,11 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
       tmem_ld32(tmem_acc + (static_cast<uint32_t>(wig * 32) << 16) + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32 * c]));
     tmem_wait_ld();
     tc_fence_before();
-    if (tn < n_tiles) stage_tile(tn);                    // the loads fly during the epilogue below
+    if (tnn < n_tiles) stage_tile(tnn, buf_t);           // two tiles ahead, into the buffer tile t just released
+    if (tn < n_tiles) {
+      if (tnn < n_tiles) cp_async_wait_1(); else cp_async_wait_all();   // tile tn (staged one iteration ago) has landed
+      publish_and_issue(buf_n);
+    }
     // ---- epilogue of tile t
     const long img = t / tiles_per_img;
     const int rem = static_cast<int>(t - img * tiles_per_img);
@@ -262,8 +277,8 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
       float* map = reinterpret_cast<float*>(out) + img * static_cast<long>(H) * W;
       map[static_cast<long>(y0 + (m >> 3)) * W + x0 + (m & 7)] = s;
     }
-    if (tn < n_tiles) publish_and_issue();
     t = tn;
+    ++it;
   }
   tc_fence_before();
   __syncthreads();

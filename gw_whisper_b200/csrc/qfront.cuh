@@ -802,6 +802,40 @@ qadapter_pool_kernel(const float* __restrict__ map, float* __restrict__ out_f32,
     }
     __syncthreads();
   }
+  // Time-major 16-bit output (the encoder's input), fast path: 3000 output columns come from only 128 source
+  // columns, so consecutive output columns repeat -- an output column is determined by its source range
+  // [ts, te) (one or two columns).  Each distinct column vector is computed once (same expression and summation
+  // order as below) and the rows are then streamed out with 16-byte stores.
+  __shared__ __align__(16) float vecs[16 * 128];        // [class][OF], class = (ts - c0) * 2 + (te - ts - 1)
+  const bool fast_tm = staged && outtm != nullptr && out32 == nullptr && (OF % 8) == 0 && nc <= 8 && W <= OT;
+  if (fast_tm) {
+    for (int i = threadIdx.x; i < 2 * nc * OF; i += 256) {
+      const int cls = i / OF, f = i - cls * OF;
+      const int xs = c0 + (cls >> 1), xe = xs + 1 + (cls & 1);
+      float v = 0.f;
+      if (xe <= c1) {
+        const int fs = frange[f].x, fe = frange[f].y;
+        float sum = 0.f;
+        for (int y = fs; y < fe; ++y)
+          for (int x = xs; x < xe; ++x) sum += cols[y * 9 + (x - c0)];
+        v = sum / static_cast<float>((fe - fs) * (xe - xs));
+        v = ad.scale * v + ad.bias;
+        v = v * g + be;
+      }
+      vecs[cls * 128 + f] = v;
+    }
+    __syncthreads();
+    const int of8 = OF / 8;
+    for (int idx = threadIdx.x; idx < of8 * (t1 - t0); idx += 256) {
+      const int tt = idx / of8, f8 = idx - tt * of8;
+      const int ts = trange[tt].x, te = trange[tt].y;
+      const float* v = vecs + ((ts - c0) * 2 + (te - ts - 1)) * 128 + 8 * f8;
+      uint4 pk;
+      pk.x = pack_op16x2(v[0], v[1]); pk.y = pack_op16x2(v[2], v[3]);
+      pk.z = pack_op16x2(v[4], v[5]); pk.w = pack_op16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(outtm + static_cast<long>(t0 + tt + 1) * OF + 8 * f8) = pk;
+    }
+  } else
   for (int idx = threadIdx.x; idx < OF * (t1 - t0); idx += 256) {
     const int tt = idx / OF, f = idx - tt * OF;          // f fastest: coalesced time-major stores
     const int t = t0 + tt;

@@ -15,8 +15,27 @@ from .encoder import B200WhisperEncoder
 
 
 def _linears(seq: nn.Sequential):
-    return [(m.weight, m.bias if m.bias is not None else torch.zeros(m.out_features)) for m in seq
-            if isinstance(m, nn.Linear)]
+    """(weight, bias) of the Linear layers of a Linear-ReLU-...-Linear head for the C ABI (which applies ReLU
+    between consecutive entries).  Two Linear layers with NO activation between them -- the Efficiency_test tail
+    Linear(64, 2) -> Linear(2, 2, bias=False), test_network.py:89-99 -- are composed into one (W2 W1, W2 b1 + b2)."""
+    out = []
+    prev_was_linear = False
+    for m in seq:
+        if isinstance(m, nn.Linear):
+            w = m.weight.detach().float().cpu()
+            b = m.bias.detach().float().cpu() if m.bias is not None else torch.zeros(m.out_features)
+            if prev_was_linear:
+                w0, b0 = out.pop()
+                w, b = w @ w0, w @ b0 + b
+            out.append((w, b))
+            prev_was_linear = True
+        elif isinstance(m, (nn.ReLU,)):
+            prev_was_linear = False
+        elif isinstance(m, (nn.Dropout, nn.Softmax, nn.Identity)):
+            pass                                   # inert in eval / handled by the softmax flag
+        else:
+            raise TypeError(f"unsupported layer in a classifier head: {type(m).__name__}")
+    return out
 
 
 def replace_softmax_by_mutual_subtraction(network) -> None:

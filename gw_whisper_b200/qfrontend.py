@@ -216,7 +216,8 @@ class GWWhisperClassifier(nn.Module):
 
     def _sync_head(self) -> None:
         if self._head_dirty or self.encoder._head_key != id(self):
-            lin = [(m.weight, m.bias) for m in self.classifier if isinstance(m, nn.Linear)]
+            from .models import _linears
+            lin = _linears(self.classifier)
             softmax = any(isinstance(m, nn.Softmax) for m in self.classifier)
             self.encoder.set_head(lin, softmax=softmax)
             self.encoder._head_key = id(self)

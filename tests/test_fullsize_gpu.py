@@ -69,3 +69,45 @@ def test_stream_search_equals_explicit_windows_and_host_threshold():
     s2, i2, _ = LogMelStreamNetwork(model).stream_search(seg, HOP, 300, thr, first_window=500)
     assert torch.equal(s2, ref[500:800])
     assert torch.equal(i2, keep[(keep >= 500) & (keep < 800)])   # trigger indices are global window indices
+
+
+def test_sharded_search_world1_and_emulated_ranks_equal_the_single_stream():
+    """sharding.sharded_search on the GPU: with world=1 it must return exactly what one
+    stream_search per segment returns; and the union of the pieces every rank of a 3-rank plan would compute
+    (each piece handed only its sample range + halo) must reproduce the same scores bit for bit --
+    including ragged segments and, for the MLGWSC-1 model, the batch-coupled QScan plane choice (whole
+    256-window batches per shard)."""
+    from gw_whisper_b200 import B200WhisperEncoder, GWWhisperClassifier, QTransformAdapter, sharding
+    from gw_whisper_b200 import synthetic as S
+    dev = torch.device("cuda")
+    base = S.make_encoder("tiny", 0, spread=True)
+    enc = B200WhisperEncoder.from_hf(base, dora=S.synthetic_dora("tiny", targets=("q_proj", "k_proj", "v_proj", "out_proj")),
+                                     chunk=512)
+    torch.manual_seed(11)
+    model = GWWhisperClassifier(enc, 2, num_classes=2, q_adapter=QTransformAdapter(n_detectors=2))
+    S.seeded_head(model.classifier, seed=3, gain=3.0)
+    model.refresh()
+    g = torch.Generator().manual_seed(5)
+    lens = [2048 + HOP * 700, 2048 + HOP * 255 + 17, 2048 + HOP * 256, 3000, 1000]      # ragged, one too short
+    segs = [torch.randn(2, n, generator=g).to(dev) for n in lens]
+    nws = [sharding.n_windows(n, HOP) for n in lens]
+    thr = 0.5
+    (seg, idx, sc), scores = sharding.sharded_search(model, segs, HOP, thr, 0, 1)
+    assert [int(s.numel()) for s in scores] == nws
+    for i, s in enumerate(segs):
+        if nws[i] == 0:
+            continue
+        ref, ridx, rsc = model.stream_search(s, HOP, nws[i], thr)
+        assert torch.equal(scores[i], ref)
+        assert torch.equal(idx[seg == i], ridx) and torch.equal(sc[seg == i], rsc)
+    # emulate a 3-rank run in this process: every rank's pieces, merged by hand
+    plan = sharding.plan_shards(nws, 3)
+    assert all(len(p) > 0 for p in plan)
+    merged = [torch.full((n,), float("nan"), device=dev) for n in nws]
+    for pieces in plan:
+        for p in pieces:
+            lo, hi = p.sample_range(HOP)
+            part, _, _ = model.stream_search(segs[p.segment][:, lo:hi].contiguous(), HOP, p.n_windows, thr)
+            merged[p.segment][p.first_window:p.first_window + p.n_windows] = part
+    for a, b in zip(merged, scores):
+        assert torch.equal(a, b)
