@@ -544,7 +544,9 @@ def run_b200(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     ncu_traffic = {}
-    tr_path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    tr_path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(tr_path):
+        tr_path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
     if os.path.exists(tr_path):
         ncu_traffic = json.load(open(tr_path))
 
@@ -559,9 +561,12 @@ def run_b200(args):
         n_chunks = -(-n_dw // args.chunk)
         return ent["dram_bytes_per_launch"] * (n_dw / n_chunks) / ent["det_windows"]
 
+    traffic_src = (f"{ncu_traffic.get('source', 'profiles/' + os.path.basename(tr_path))}; dram read+write bytes per launch "
+                   "of that capture scaled to this run's det-windows per launch (not measured in this run)") if ncu_traffic else None
     roofline_gemm = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all encoder GEMMs)", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": {k: traffic_of(k) for k in ("gemm_qkv", "gemm_out_proj", "gemm_fc1", "gemm_fc2")},
+                     "traffic_source": traffic_src,
                      "peak_source": peak_src, "flops_per_launch": gemm_flops / max(gemm_launches, 1),
                      "avg_launch_ms": gemm_ms / max(gemm_launches, 1)}
     # the single kernel with the largest share of the step is the fused attention
@@ -571,14 +576,14 @@ def run_b200(args):
     att_tf = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "attention_persist_kernel (tcgen05 QK^T / PV, softmax on MUFU)",
                 "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf,
-                "traffic": traffic_of("attention_tc_kernel"),
+                "traffic": traffic_of("attention_persist_kernel"), "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": args.chunk * 1500 * (3 * d + d) * 2,
                 "peak_source": peak_src, "flops_per_launch": att_flops / max(att_n, 1),
                 "avg_launch_ms": att_ms / max(att_n, 1), "share_of_step": att_ms / max(sum(ms_k), 1e-9),
-                "note": "head_dim 64: one exp per 128 MAC, so the softmax (MUFU.EX2 16/clk/SM, sharing the XU pipe with the "
-                        "bf16 packing) needs >= 2x the tensor time of a tile: the tensor-pipe ceiling of this kernel is "
-                        "~45% of peak (profiles/r1_ubench_softmax_mix.txt: 12.7 of 16 exp/clk/SM is the instruction-mix "
-                        "ceiling at two softmax warps per sub-partition; ncu: XU 68%, tensor 34% active)"}
+                "note": "head_dim 64: one exp per 128 MAC, so the softmax (MUFU.EX2 16/clk/SM) needs >= 2x the tensor time "
+                        "of a tile: the tensor-pipe ceiling of this kernel is ~45% of peak (profiles/r2_ubench_softmax_mix2.txt: "
+                        "12.6 exp/clk/SM is the instruction-mix ceiling at two softmax warps per sub-partition, 15.1 with 2 of 8 "
+                        "pairs on the FMA-pipe polynomial, which the kernel uses since round 2)"}
     if "logmel" in kernels:
         lm_bytes = (2048 * 4 + 3002 * 80 * 2) * n_dw   # fused path writes bf16 time-major features
         kernels["logmel"]["gbs"] = lm_bytes / (kernels["logmel"]["ms_per_step"] * 1e-3) / 1e9
@@ -608,13 +613,16 @@ def run_b200(args):
         if rank == 0 and world == 1:
             torch.cuda.empty_cache()
             extras["glitch_small"] = glitch_record(args, dev, lib)
+    operand = lib.gww_operand_dtype().decode()
     if rank == 0:
         line = {
             "metric": "strain-seconds searched/sec", "value": value, "unit": "strain-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": operand, "data": "synthetic",
             "config": {"workload": f"Signal_vs_Noise two-detector classifier, whisper-{args.model} encoder + DoRA(q,k,v) "
                                    "+ 4-layer head, log-mel front end, 1 s windows @2048 Hz, hop 204",
+                       "operands": f"{operand} tensor-core operands (tcgen05 kind::f16), fp32 accumulation / residual stream / "
+                                   "softmax, f64 log-mel front end",
                        "windows_per_step_per_gpu": B, "detectors": D, "det_windows_per_chunk": args.chunk,
                        "parallelism": f"time-shard dp{world}",
                        "final_layer": ("last token only: all tokens' K/V, one query row (exact; the reference consumes "
