@@ -8,8 +8,12 @@
 //   * M = 128 output pixels (a tile of 16 rows x 8 columns), N = Cout (32 / 64), K = 9 taps x Cin.
 //   * precision: the 1e-4 feature gate rules out plain bf16 / tf32.  Every fp32 value v is split into two bf16
 //     numbers hi = bf16(v), lo = bf16(v - hi) (16 significant bits) and the product is formed as
-//     hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM: three MMAs per (tap, 16-channel K step), relative
-//     error ~1e-5 per product (the dropped lo*lo term is 2^-18), measured 1e-5 on the features (tests).
+//     hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM, relative error ~1e-5 per product (the dropped lo*lo
+//     term is 2^-18), measured 1.3e-5 on the features (tests).  The three terms take TWO MMAs per (tap, 16-channel
+//     K step): A_hi x [W_hi | W_lo] with the hi and lo weights concatenated along N (two accumulator column blocks,
+//     summed in the epilogue) and A_lo x W_hi into the first block.  These small-N MMAs are bound by the tensor
+//     core's shared-memory operand fetch (a 4 KB A tile per MMA against 16-32 clocks of math), so one A read less
+//     per step is worth 25 % (r2 launch list: conv2 was at 2.7x its math time).
 //   * no im2col: the haloed input tile (18 x 10 pixels) is staged once in shared memory as PLANES of 16-byte
 //     elements -- plane p holds 8 consecutive channels (hi or lo) of every pixel, pixel-major.  In the
 //     no-swizzle K-major canonical layout of the UMMA shared-memory descriptor (8 rows x 16 B core matrices,
@@ -46,7 +50,8 @@ struct QtCfg {
   static constexpr int kGroups = (CIN == 16) ? 6 : 3;     // shared memory (two staging buffers per group) and registers
   static constexpr int kBufs = 2;                         // staging buffers per group: tile t+2 loads while t+1 computes
   static constexpr int kThreads = kGroups * kQtGroupThreads;
-  static constexpr int kTmemCols = (kGroups * COUT <= 256) ? 256 : 512;
+  static constexpr int kAccCols = 2 * COUT;               // [A_hi W_hi + A_lo W_hi | A_hi W_lo]
+  static constexpr int kTmemCols = (kGroups * kAccCols <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kWBytes + kGroups * kBufs * kTileBytes + COUT * 8 + 64 + kGroups * 8 + 16;
 };
 
@@ -80,16 +85,16 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 }
 
 // Weights of a 3x3 convolution, host layout [tap][ci][co] fp32 (as uploaded for the fp32 kernels), packed once
-// per model into the shared-memory image: element ((tap * kPlanes + plane) * COUT + co) holds channels
-// 8*chunk .. 8*chunk+7 of output channel co as bf16 (plane < kChunks: hi, else lo).
+// per model into the shared-memory image: element (((tap * kChunks + chunk) * 2 + hl) * COUT + co) holds channels
+// 8*chunk .. 8*chunk+7 of output channel co as bf16 (hl = 0: hi, 1: lo), i.e. per (tap, chunk) a [2*COUT] x 16 B
+// K-major operand whose first COUT rows are W_hi and whose last COUT rows are W_lo.
 template <int CIN, int COUT>
 __global__ void qt_pack_weights_kernel(const float* __restrict__ w, uint4* __restrict__ out) {
   using Cfg = QtCfg<CIN, COUT>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cfg::kWElems) return;
-  const int co = i % COUT, plane = (i / COUT) % Cfg::kPlanes, tap = i / (COUT * Cfg::kPlanes);
-  const int chunk = plane % Cfg::kChunks;
-  const bool want_lo = plane >= Cfg::kChunks;
+  const int co = i % COUT, hl = (i / COUT) & 1, chunk = (i / (2 * COUT)) % Cfg::kChunks, tap = i / (2 * COUT * Cfg::kChunks);
+  const bool want_lo = hl != 0;
   uint32_t r[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -141,7 +146,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(grp * COUT);   // this group's accumulator columns
+  const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(grp * Cfg::kAccCols);   // this group's accumulator columns
   const uint32_t bar = smem_u32(&bars[grp]);
   const uint32_t tile_addr0 = smem_u32(tiles + grp * Cfg::kBufs * Cfg::kTileBytes);   // buffer b at + b * kTileBytes
   const uint32_t w_addr = smem_u32(w_s);
@@ -150,24 +155,21 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   const long tiles_per_img = static_cast<long>(tiles_x) * tiles_y;
   const long n_tiles = tiles_per_img * n_img;
   const long stride = static_cast<long>(gridDim.x) * Cfg::kGroups;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, COUT);
+  constexpr uint32_t kIdescWide = make_idesc_bf16(128, 2 * COUT), kIdescNarrow = make_idesc_bf16(128, COUT);
   auto issue_mmas = [&](const uint32_t tile_addr) {
-    // three split terms: (A hi, W hi), (A lo, W hi), (A hi, W lo); per tap, per pair of 8-channel chunks (K = 16)
+    // per tap and pair of 8-channel chunks (K = 16):  D[:, 0:2C] (+)= A_hi x [W_hi | W_lo] ;  D[:, 0:C] += A_lo x W_hi
     uint32_t first = 1;
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
       const uint32_t shift = static_cast<uint32_t>(((tap / 3) * kQtHaloW + (tap % 3)) * 16);
 #pragma unroll
       for (int kp = 0; kp < Cfg::kChunks / 2; ++kp) {
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const int a_plane = (term == 1 ? Cfg::kChunks : 0) + 2 * kp;
-          const int w_plane = (term == 2 ? Cfg::kChunks : 0) + 2 * kp;
-          const uint64_t adesc = make_nosw_desc(tile_addr + a_plane * kQtPlaneBytes + shift, kQtPlaneBytes, kQtHaloW * 16);
-          const uint64_t bdesc = make_nosw_desc(w_addr + ((tap * Cfg::kPlanes + w_plane) * COUT) * 16, COUT * 16, 128);
-          umma_ss(tmem_acc, adesc, bdesc, kIdesc, first ? 0u : 1u);
-          first = 0;
-        }
+        const uint64_t a_hi = make_nosw_desc(tile_addr + (2 * kp) * kQtPlaneBytes + shift, kQtPlaneBytes, kQtHaloW * 16);
+        const uint64_t a_lo = make_nosw_desc(tile_addr + (Cfg::kChunks + 2 * kp) * kQtPlaneBytes + shift, kQtPlaneBytes, kQtHaloW * 16);
+        const uint64_t bdesc = make_nosw_desc(w_addr + ((tap * Cfg::kChunks + 2 * kp) * 2 * COUT) * 16, 2 * COUT * 16, 128);
+        umma_ss(tmem_acc, a_hi, bdesc, kIdescWide, first ? 0u : 1u);
+        umma_ss(tmem_acc, a_lo, bdesc, kIdescNarrow, 1u);
+        first = 0;
       }
     }
   };
@@ -223,9 +225,14 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
     tc_fence_after();
     uint32_t acc[COUT];
 #pragma unroll
-    for (int c = 0; c < COUT / 32; ++c)
+    for (int c = 0; c < COUT / 32; ++c) {
+      uint32_t lo_blk[32];
       tmem_ld32(tmem_acc + (static_cast<uint32_t>(wig * 32) << 16) + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32 * c]));
-    tmem_wait_ld();
+      tmem_ld32(tmem_acc + (static_cast<uint32_t>(wig * 32) << 16) + COUT + c * 32, lo_blk);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[32 * c + i] = __float_as_uint(__uint_as_float(acc[32 * c + i]) + __uint_as_float(lo_blk[i]));
+    }
     tc_fence_before();
     if (tnn < n_tiles) stage_tile(tnn, buf_t);           // two tiles ahead, into the buffer tile t just released
     if (tn < n_tiles) {
