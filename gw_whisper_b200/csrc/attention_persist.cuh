@@ -58,6 +58,21 @@ constexpr int kApLookahead = GWW_AP_LOOKAHEAD;
 #ifndef GWW_AP_POLY
 #define GWW_AP_POLY 2
 #endif
+// GWW_AP_MMA_WARPS = 2: one MMA-issuing warp per query tile (warps 9 and 10, two different sub-partitions), each a
+// static sequence S(0), [S(m), P.V(m-1)]..., P.V(last) on blocking mbarrier waits -- within one query tile "S copied
+// out" always precedes "P written", so the static order is the event order.  Why (profiles/r2_attn_trace.txt): the
+// softmax warps' MUFUs go through the same in-order MIO queue of a sub-partition as the issuer's mbarrier and tcgen05
+// instructions; a ready mbarrier test costs the issuer 70-230 clk and one block of 4-8 tcgen05.mma + commits ~450 clk
+// (measured by letting the softmax warps issue: -DGWW_AP_TRACE variants of this round).  A single event-driven
+// issuer therefore needs ~600 clk per event x 4 events (S0, S1, PV0, PV1) of every ~2870-clk tile period: it is
+// ~85 % busy, and "P written" -> "P.V finished" took 1000-1900 clk for 256 clk of tensor work.  1 = that single
+// event-driven issuer (round 1).
+#ifndef GWW_AP_MMA_WARPS
+#define GWW_AP_MMA_WARPS 2
+#endif
+#ifndef GWW_AP_EARLY_TEST
+#define GWW_AP_EARLY_TEST 1   // softmax warps test sfull(n+1) / pvdone(n-1) ahead of use (non-blocking)
+#endif
 #ifndef GWW_ATTN_POLL_NS
 #define GWW_ATTN_POLL_NS 64   // back-off of the MMA warp's polling loop when nothing is ready
 #endif
@@ -126,7 +141,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_qfull + 8 * i, 1);
-      mbar_init(bar_qempty + 8 * i, 1);
+      mbar_init(bar_qempty + 8 * i, GWW_AP_MMA_WARPS);        // one commit per issuing warp
       mbar_init(bar_sfull + 8 * i, 1);
       mbar_init(bar_sfree + 8 * i, 4);       // one elected arrival per softmax warp
       mbar_init(bar_pfull + 8 * i, 4);
@@ -136,9 +151,9 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
     }
     for (int i = 0; i < kApStages; ++i) {
       mbar_init(bar_kfull + 8 * i, 1);
-      mbar_init(bar_kempty + 8 * i, 1);
+      mbar_init(bar_kempty + 8 * i, GWW_AP_MMA_WARPS);
       mbar_init(bar_vfull + 8 * i, 1);
-      mbar_init(bar_vempty + 8 * i, 1);
+      mbar_init(bar_vempty + 8 * i, GWW_AP_MMA_WARPS);
     }
     fence_mbar_init();
   }
@@ -186,6 +201,62 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
           if (++stage == kApStages) { stage = 0; phase ^= 1; }
         }
       }
+#if GWW_AP_MMA_WARPS == 2
+    } else if (warp == 9 || warp == 10) {
+      // ===================== MMA issuer of query tile t: static order, blocking waits =====================
+      const int t = warp - 9;
+      constexpr uint32_t kIdescS = make_idesc_op16(128, 128, 0);
+      constexpr uint32_t kIdescO = make_idesc_op16(128, 64, 1);   // V is MN-major
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
+      const uint32_t tS = tb + t * 128, tP = tb + 256 + t * 64, tO = tb + 384 + t * 64;
+      const uint32_t q_smem = smem_u32(q_s) + t * 16384, k_smem = smem_u32(k_s), v_smem = smem_u32(v_s);
+      const uint32_t b_sfull = bar_sfull + 8 * t, b_sfree = bar_sfree + 8 * t;
+      const uint32_t b_pfull = bar_pfull + 8 * t, b_pvdone = bar_pvdone + 8 * t;
+      const int total = n_local * nkv;
+      int s_k = 0, s_j = 0, s_stage = 0, pv_k = 0, pv_j = 0, pv_stage = 0;
+      uint32_t s_phase = 0, pv_phase = 0;
+      for (int m = 0; m <= total; ++m) {
+        if (m < total) {
+          // ---- S(m) = Q.K^T of tile m: K tile resident, S(m-1) copied out, (first tile of an item) Q resident
+          // (the barrier that completes last is waited for last: every wait, even on a completed barrier, is a
+          //  round trip through the MIO queue behind the softmax warps' MUFUs)
+          if (s_j == 0) mbar_wait(bar_qfull + 8 * (s_k & 1), (s_k >> 1) & 1);
+          if (m > 0) mbar_wait2(bar_kfull + 8 * s_stage, s_phase, b_sfree, (m - 1) & 1);
+          else mbar_wait(bar_kfull + 8 * s_stage, s_phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t qdesc = make_sw128_desc(q_smem + (s_k & 1) * 32768);
+            const uint64_t kdesc = make_sw128_desc(k_smem + s_stage * 16384);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ss(tS, qdesc + 2 * kk, kdesc + 2 * kk, kIdescS, kk);
+            umma_commit(b_sfull);
+            umma_commit(bar_kempty + 8 * s_stage);                    // second arrival: the other tile's issuer
+            if (s_j + 1 == nkv) umma_commit(bar_qempty + 8 * (s_k & 1));
+          }
+          __syncwarp();
+          if (++s_j == nkv) { s_j = 0; ++s_k; }
+          if (++s_stage == kApStages) { s_stage = 0; s_phase ^= 1; }
+        }
+        if (m > 0) {
+          // ---- O += P(m-1).V(m-1): V tile resident, P written, (first tile of an item) previous O read out
+          if (pv_j == 0 && pv_k > 0) mbar_wait(bar_ofree + 8 * t, (pv_k - 1) & 1);
+          mbar_wait2(bar_vfull + 8 * pv_stage, pv_phase, b_pfull, (m - 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t vdesc = make_sw128_desc(v_smem + pv_stage * 16384);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ts(tO, tP + 8 * kk, vdesc + 128 * kk, kIdescO, (pv_j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(b_pvdone);
+            umma_commit(bar_vempty + 8 * pv_stage);
+            if (pv_j + 1 == nkv) umma_commit(bar_ofull + 8 * t);
+          }
+          __syncwarp();
+          if (++pv_j == nkv) { pv_j = 0; ++pv_k; }
+          if (++pv_stage == kApStages) { pv_stage = 0; pv_phase ^= 1; }
+        }
+      }
+#else
     } else if (warp == 9) {
       // ===================== MMA issuer (event driven, see attention_tc.cuh) =====================
       constexpr uint32_t kIdescS = make_idesc_op16(128, 128, 0);
@@ -267,6 +338,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
           }
         }
       }
+#endif
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -282,6 +354,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
     const uint32_t b_sfull = bar_sfull + 8 * t, b_sfree = bar_sfree + 8 * t;
     const uint32_t b_pfull = bar_pfull + 8 * t, b_pvdone = bar_pvdone + 8 * t;
     int n = 0;                                  // key tiles processed so far (barrier parities)
+    bool s_early = false;                       // "S of tile n is ready" already observed
     AP_TRACE(long long w_sfull = 0; long long w_pv = 0; long long w_ofull = 0; long long w_ld = 0; long long w_exp = 0;)
     AP_TRACE(long long w_max = 0; long long w_tail = 0; long long w_epi = 0;)
     AP_TRACE(const long long c_begin = clock64(); const unsigned long long ns_begin = globaltimer_ns();)
@@ -290,7 +363,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
     auto tile = [&](const int j, auto mask_tag) {
       constexpr bool kMask = decltype(mask_tag)::value;
       AP_TRACE(long long c0 = clock64();)
-      mbar_wait(b_sfull, n & 1);
+      if (!s_early) mbar_wait(b_sfull, n & 1);     // usually already seen complete by the test inside the previous tile
       AP_TRACE(long long c1 = clock64(); w_sfull += c1 - c0;)
       tc_fence_after();
       uint32_t s[4][32];
@@ -347,6 +420,8 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
           if (need) m_used = mt;
         }
       }
+      // non-blocking look at "P(n-1).V finished" after the first 32 exponentials, consumed after 64
+      uint32_t pv_early = 0u;
       const float mneg = -m_used * kLog2e;
       float l0 = 0.f, l1 = 0.f;
       uint32_t pk[32];
@@ -386,10 +461,12 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
 #endif
           pk[(c & 1) * 16 + (i >> 1)] = pack_op16x2(p0, p1);
         }
+        if (GWW_AP_EARLY_TEST && c == 0) pv_early = mbar_test(b_pvdone, (n - 1) & 1);   // unconditional: result unused at j == 0
+        if (GWW_AP_EARLY_TEST && c == 2) s_early = __all_sync(0xffffffffu, mbar_test(b_sfull, (n + 1) & 1));   // S of the next tile
         if (c & 1) {                                 // 64 keys packed -> 32 TMEM columns of P: half c >> 1
           if (!pv_waited) {
             AP_TRACE(long long c3 = clock64();)
-            mbar_wait(b_pvdone, (n - 1) & 1);        // P_t(n-1).V finished reading P_t
+            if (!__all_sync(0xffffffffu, pv_early)) mbar_wait(b_pvdone, (n - 1) & 1);   // P_t(n-1).V finished reading P_t
             AP_TRACE(long long c4 = clock64(); w_pv += c4 - c3; c2 += c4 - c3;)
             tc_fence_after();
             pv_waited = true;
@@ -452,11 +529,11 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,  // {3d, T, 
       AP_TRACE(w_epi += clock64() - c5b;)
     }
     if (lane == 0) tma_store_wait_all<0>();
-    AP_TRACE(if (blockIdx.x < 3 && threadIdx.x == 0) {
+    AP_TRACE(if (blockIdx.x < 1 && lane == 0) {
       const long long cyc = clock64() - c_begin;
       const unsigned long long ns = globaltimer_ns() - ns_begin;
-      printf("gww-trace block=%d tiles=%d cycles=%lld ns=%llu MHz=%.0f per-tile: total=%.0f sfull_wait=%.0f tmem_ld=%.0f max+rescale=%.0f exp_phase=%.0f (pvdone_wait=%.0f) tail=%.0f | per item: ofull_wait=%.0f epilogue=%.0f\n",
-             blockIdx.x, n, cyc, ns, 1e3 * (double)cyc / (double)ns, (double)cyc / n, (double)w_sfull / n, (double)w_ld / n,
+      printf("gww-trace block=%d warp=%d tiles=%d cycles=%lld ns=%llu MHz=%.0f per-tile: total=%.0f sfull_wait=%.0f tmem_ld=%.0f max+rescale=%.0f exp_phase=%.0f (pvdone_wait=%.0f) tail=%.0f | per item: ofull_wait=%.0f epilogue=%.0f\n",
+             blockIdx.x, warp, n, cyc, ns, 1e3 * (double)cyc / (double)ns, (double)cyc / n, (double)w_sfull / n, (double)w_ld / n,
              (double)w_max / n, (double)w_exp / n, (double)w_pv / n, (double)w_tail / n, (double)w_ofull / n_local, (double)w_epi / n_local);
     })
   }

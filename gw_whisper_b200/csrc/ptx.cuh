@@ -112,6 +112,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Waits for two barriers; both tests are in flight together (one round trip when both have completed).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b) {
+  const uint32_t a = mbar_test(bar_a, parity_a), b = mbar_test(bar_b, parity_b);
+  if (!a) mbar_wait(bar_a, parity_a);
+  if (!b) mbar_wait(bar_b, parity_b);
+}
+
 // One lane of a CONVERGED warp (all 32 lanes must execute this).  Single-thread instruction streams
 // (TMA issue, tcgen05.mma issue) are written as warp-uniform loops with `if (elect_one()) {...}`:
 // ptxas then keeps the whole loop in the uniform datapath and emits bare UTMALDG / UTCHMMA.  The

@@ -1,11 +1,15 @@
 #!/bin/bash
-# one gpurun call of round 2 (edited per call): logs go to gpurun_out/
 mkdir -p gpurun_out
-NCU="ncu --set full --clock-control none --import-source on -f"
-python tools/profile_step.py --windows 128 > gpurun_out/r2_profile_step.log 2>&1 || exit 1
-python tools/profile_mlgwsc.py > gpurun_out/r2_profile_mlgwsc.log 2>&1 || exit 1
-$NCU -k regex:attention_persist_kernel -s 1 -c 1 -o gpurun_out/r2_ncu_attn python tools/profile_step.py --windows 128 > gpurun_out/r2_ncu_attn.log 2>&1
-$NCU -k regex:logmel_kernel -s 1 -c 1 -o gpurun_out/r2_ncu_logmel python tools/profile_step.py --windows 128 > gpurun_out/r2_ncu_logmel.log 2>&1
-$NCU -k regex:gemm_tc_kernel -s 6 -c 4 -o gpurun_out/r2_ncu_gemm python tools/profile_step.py --windows 128 > gpurun_out/r2_ncu_gemm.log 2>&1
-$NCU -k regex:"qadapter_conv|qscan_tiles|qadapter_pool|qscan_interp" -s 6 -c 6 -o gpurun_out/r2_ncu_qfront python tools/profile_mlgwsc.py > gpurun_out/r2_ncu_qfront.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k attention 2>&1 | tail -5
+out=gpurun_out/r2_attn_mw3.jsonl; : > $out
+python tools/attn_bench.py --reps 20 >> $out 2>gpurun_out/r2_attn_mw.err
+for v in g0 e0; do
+  GWW_LIB=gw_whisper_b200/variants/lib_$v.so timeout 120 python tools/attn_bench.py --reps 20 >> $out 2>>gpurun_out/r2_attn_mw.err
+done
+python tools/attn_bench.py --reps 20 --d 384 >> $out 2>>gpurun_out/r2_attn_mw.err
+python tools/attn_bench.py --reps 20 --d 768 --det-windows 128 >> $out 2>>gpurun_out/r2_attn_mw.err
+cat $out
+for v in tr; do
+GWW_LIB=gw_whisper_b200/variants/lib_$v.so timeout 120 python tools/attn_bench.py --reps 1 --warmup 0 --det-windows 74 2>&1 | grep "gww-" | cut -c1-360 | sort > gpurun_out/r2_attn_trace_$v.txt
+cat gpurun_out/r2_attn_trace_$v.txt
+done
