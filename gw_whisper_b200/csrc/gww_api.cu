@@ -1626,16 +1626,27 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
     const int sms = g_num_sms;
     const int grid2 = (int)std::min<long>(sms, (tiles2 + C2::kGroups - 1) / C2::kGroups);
     const int grid3 = (int)std::min<long>(sms, (tiles3 + C3::kGroups - 1) / C3::kGroups);
+    // the plane-format activations as 4-D maps {4 W words, H, planes, n}: one haloed tile = one TMA box
+    CUtensorMap tm2, tm3;
+    {
+      const int H2 = F / 2, W2 = T / 2, H3 = F / 4, W3 = T / 4;
+      const uint64_t d2[4] = {(uint64_t)4 * W2, (uint64_t)H2, (uint64_t)C2::kPlanes, (uint64_t)n};
+      const uint64_t s2[3] = {(uint64_t)16 * W2, (uint64_t)16 * W2 * H2, (uint64_t)16 * W2 * H2 * C2::kPlanes};
+      const uint32_t b2[4] = {4 * kQtHaloW, kQtHaloH, (uint32_t)C2::kPlanes, 1};
+      GWW_TRY(make_map(&tm2, true, 4, ws.act1, d2, s2, b2, false));
+      const uint64_t d3[4] = {(uint64_t)4 * W3, (uint64_t)H3, (uint64_t)C3::kPlanes, (uint64_t)n};
+      const uint64_t s3[3] = {(uint64_t)16 * W3, (uint64_t)16 * W3 * H3, (uint64_t)16 * W3 * H3 * C3::kPlanes};
+      const uint32_t b3[4] = {4 * kQtHaloW, kQtHaloH, (uint32_t)C3::kPlanes, 1};
+      GWW_TRY(make_map(&tm3, true, 4, ws.act2, d3, s3, b3, false));
+    }
     {
       ProfScope ps(PK_QA_CONV2, s);
-      k2<<<grid2, C2::kThreads, C2::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act1), qf->ad.w2p, qf->ad.b2, nullptr, 0.f,
-                                                    ws.act2, F / 2, T / 2, n);
+      k2<<<grid2, C2::kThreads, C2::kSmemBytes, s>>>(tm2, qf->ad.w2p, qf->ad.b2, nullptr, 0.f, ws.act2, F / 2, T / 2, n);
     }
     LAUNCH_CHECK();
     {
       ProfScope ps(PK_QA_CONV3, s);
-      k3<<<grid3, C3::kThreads, C3::kSmemBytes, s>>>(reinterpret_cast<const uint4*>(ws.act2), qf->ad.w3p, qf->ad.b3, qf->ad.w4,
-                                                    qf->ad.b4, ws.map, F / 4, T / 4, n);
+      k3<<<grid3, C3::kThreads, C3::kSmemBytes, s>>>(tm3, qf->ad.w3p, qf->ad.b3, qf->ad.w4, qf->ad.b4, ws.map, F / 4, T / 4, n);
     }
     LAUNCH_CHECK();
   } else {

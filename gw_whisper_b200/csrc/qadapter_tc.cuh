@@ -52,7 +52,7 @@ struct QtCfg {
   static constexpr int kThreads = kGroups * kQtGroupThreads;
   static constexpr int kAccCols = 2 * COUT;               // [A_hi W_hi + A_lo W_hi | A_hi W_lo]
   static constexpr int kTmemCols = (kGroups * kAccCols <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kWBytes + kGroups * kBufs * kTileBytes + COUT * 8 + 64 + kGroups * 8 + 16;
+  static constexpr int kSmemBytes = kWBytes + kGroups * kBufs * kTileBytes + COUT * 8 + 64 + kGroups * 8 * (1 + kBufs) + 16;
 };
 
 // no-swizzle K-major shared-memory matrix descriptor (see header comment)
@@ -114,7 +114,8 @@ __global__ void qt_pack_weights_kernel(const float* __restrict__ w, uint4* __res
 // ------------------------------------------------------------------------------------------------
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(QtCfg<CIN, COUT>::kThreads, 1)
-qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ wpacked, const float* __restrict__ bias,
+qadapter_conv_tc_kernel(const __grid_constant__ CUtensorMap tmIn,   // {4 W (u32), H, kPlanes, n} box {40, 18, kPlanes, 1}
+                        const uint4* __restrict__ wpacked, const float* __restrict__ bias,
                         const float* __restrict__ w4, float b4, void* __restrict__ out, int H, int W, long n_img) {
   using Cfg = QtCfg<CIN, COUT>;
   extern __shared__ __align__(128) uint8_t qt_smem[];
@@ -123,7 +124,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   float* bias_s = reinterpret_cast<float*>(tiles + Cfg::kGroups * Cfg::kBufs * Cfg::kTileBytes);
   float* w4_s = bias_s + COUT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w4_s + COUT + 16);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::kGroups);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::kGroups * (1 + Cfg::kBufs));   // [grp]: MMAs done; then [grp][buf]: tile landed
 
   const int tid = threadIdx.x;
   const int grp = uniform_warp_idx() >> 2;               // 4 warps per group
@@ -135,7 +136,8 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
     bias_s[i] = bias[i];
     w4_s[i] = (MODE == 1) ? w4[i] : 0.f;
   }
-  if (tid < Cfg::kGroups) mbar_init(smem_u32(&bars[tid]), 1);
+  if (tid < Cfg::kGroups * (1 + Cfg::kBufs)) mbar_init(smem_u32(&bars[tid]), 1);
+  if (tid == 0) tma_prefetch_desc(&tmIn);
   if (uniform_warp_idx() == 0) {
     tmem_alloc<Cfg::kTmemCols>(smem_u32(tmem_slot));
     tmem_relinquish();
@@ -148,6 +150,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(grp * Cfg::kAccCols);   // this group's accumulator columns
   const uint32_t bar = smem_u32(&bars[grp]);
+  const uint32_t bar_full0 = smem_u32(&bars[Cfg::kGroups + grp * Cfg::kBufs]);                // + 8 * buffer
   const uint32_t tile_addr0 = smem_u32(tiles + grp * Cfg::kBufs * Cfg::kTileBytes);   // buffer b at + b * kTileBytes
   const uint32_t w_addr = smem_u32(w_s);
 
@@ -173,29 +176,25 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
       }
     }
   };
-  // stage the haloed tile of tile index t: 16-byte cp.async per element, zero-filled outside the image
-  auto stage_tile = [&](long t, const uint32_t tile_addr) {
+  // stage the haloed tile of tile index t into buffer b: ONE TMA box (4-D: 16-byte pixels as 4 words, rows, planes,
+  // image; out-of-image coordinates are zero-filled = the convolution's padding).  r2 ncu of the cp.async version: 720 /
+  // 1440 16-byte copies per tile with their index arithmetic were ~40 % of the kernel's instructions and kept the L1
+  // 74 % busy.  Called by one elected thread.
+  auto stage_tile = [&](long t, const int b) {
     const long img = t / tiles_per_img;
     const int rem = static_cast<int>(t - img * tiles_per_img);
     const int ty0 = (rem / tiles_x) * kQtTileH - 1, tx0 = (rem % tiles_x) * kQtTileW - 1;
-    const uint4* src = in + img * static_cast<long>(Cfg::kPlanes) * H * W;
-    for (int e = gt; e < Cfg::kPlanes * kQtPlaneElems; e += kQtGroupThreads) {
-      const int plane = e / kQtPlaneElems, pe = e - plane * kQtPlaneElems;
-      const int y = ty0 + pe / kQtHaloW, x = tx0 + pe % kQtHaloW;
-      const bool ok = (y >= 0 && y < H && x >= 0 && x < W);
-      const uint4* g = src + (static_cast<long>(plane) * H + (ok ? y : 0)) * W + (ok ? x : 0);
-      cp_async_16_zfill(tile_addr + e * 16, g, ok ? 16u : 0u);
-    }
-    cp_async_commit();
+    mbar_arrive_expect_tx(bar_full0 + 8 * b, Cfg::kTileBytes);
+    tma_load_4d(tile_addr0 + b * Cfg::kTileBytes, &tmIn, bar_full0 + 8 * b, 4 * tx0, ty0, 0, static_cast<int>(img));
   };
-  // tile staged by all 128 threads of the group + accumulator drained by its four warps -> one thread issues the MMAs
-  auto publish_and_issue = [&](const uint32_t tile_addr) {
-    fence_proxy_async_smem();
+  // accumulator drained by the group's four warps (named barrier) and tile landed (mbarrier) -> one thread issues the MMAs
+  auto publish_and_issue = [&](const int b, const uint32_t parity) {
     named_bar_sync(1 + grp, kQtGroupThreads);
     if (wig == 0) {
+      mbar_wait(bar_full0 + 8 * b, parity);
       tc_fence_after();
       if (elect_one()) {
-        issue_mmas(tile_addr);
+        issue_mmas(tile_addr0 + b * Cfg::kTileBytes);
         umma_commit(bar);
       }
       __syncwarp();
@@ -203,26 +202,30 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
   };
 
   // Software pipeline per group (two staging buffers): while the MMAs of tile t run, tile t+1 is already resident and
-  // tile t+2 is in flight (cp.async); the epilogue of tile t overlaps the MMAs of tile t+1.
+  // tile t+2 is in flight (TMA); the epilogue of tile t overlaps the MMAs of tile t+1.  Tile number `it` of the group
+  // lives in buffer it & 1, the (it >> 1)-th use of that buffer.
   long t = static_cast<long>(blockIdx.x) * Cfg::kGroups + grp;
   uint32_t phase = 0;
   int it = 0;
   if (t < n_tiles) {
-    stage_tile(t, tile_addr0);
-    if (t + stride < n_tiles) {
-      stage_tile(t + stride, tile_addr0 + Cfg::kTileBytes);
-      cp_async_wait_1();
-    } else {
-      cp_async_wait_all();
+    if (wig == 0) {
+      if (elect_one()) {
+        stage_tile(t, 0);
+        if (t + stride < n_tiles) stage_tile(t + stride, 1);
+      }
+      __syncwarp();
     }
-    publish_and_issue(tile_addr0);
+    publish_and_issue(0, 0);
   }
   while (t < n_tiles) {
     const long tn = t + stride, tnn = tn + stride;
-    const uint32_t buf_t = tile_addr0 + (it & 1) * Cfg::kTileBytes, buf_n = tile_addr0 + ((it + 1) & 1) * Cfg::kTileBytes;
     mbar_wait(bar, phase);                               // MMAs of tile t done: accumulator ready, buffer of t free
     phase ^= 1;
     tc_fence_after();
+    if (wig == 0 && tnn < n_tiles) {                     // two tiles ahead, into the buffer tile t just released
+      if (elect_one()) stage_tile(tnn, it & 1);
+      __syncwarp();
+    }
     uint32_t acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT / 32; ++c) {
@@ -234,11 +237,7 @@ qadapter_conv_tc_kernel(const uint4* __restrict__ in, const uint4* __restrict__ 
       for (int i = 0; i < 32; ++i) acc[32 * c + i] = __float_as_uint(__uint_as_float(acc[32 * c + i]) + __uint_as_float(lo_blk[i]));
     }
     tc_fence_before();
-    if (tnn < n_tiles) stage_tile(tnn, buf_t);           // two tiles ahead, into the buffer tile t just released
-    if (tn < n_tiles) {
-      if (tnn < n_tiles) cp_async_wait_1(); else cp_async_wait_all();   // tile tn (staged one iteration ago) has landed
-      publish_and_issue(buf_n);
-    }
+    if (tn < n_tiles) publish_and_issue((it + 1) & 1, static_cast<uint32_t>(((it + 1) >> 1) & 1));
     // ---- epilogue of tile t
     const long img = t / tiles_per_img;
     const int rem = static_cast<int>(t - img * tiles_per_img);

@@ -1,15 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k attention 2>&1 | tail -5
-out=gpurun_out/r2_attn_mw3.jsonl; : > $out
-python tools/attn_bench.py --reps 20 >> $out 2>gpurun_out/r2_attn_mw.err
-for v in g0 e0; do
-  GWW_LIB=gw_whisper_b200/variants/lib_$v.so timeout 120 python tools/attn_bench.py --reps 20 >> $out 2>>gpurun_out/r2_attn_mw.err
-done
-python tools/attn_bench.py --reps 20 --d 384 >> $out 2>>gpurun_out/r2_attn_mw.err
-python tools/attn_bench.py --reps 20 --d 768 --det-windows 128 >> $out 2>>gpurun_out/r2_attn_mw.err
-cat $out
-for v in tr; do
-GWW_LIB=gw_whisper_b200/variants/lib_$v.so timeout 120 python tools/attn_bench.py --reps 1 --warmup 0 --det-windows 74 2>&1 | grep "gww-" | cut -c1-360 | sort > gpurun_out/r2_attn_trace_$v.txt
-cat gpurun_out/r2_attn_trace_$v.txt
-done
+timeout 900 python -m pytest tests/test_qfront_gpu.py tests/test_mlgwsc_golden.py tests/test_train_geometry.py -m gpu -q -x -s 2>&1 | grep -v Warning | tail -15
+python bench.py --workload mlgwsc --no-cpu-baseline > gpurun_out/r2_bench_mlgwsc3.json 2> gpurun_out/r2_bench_mlgwsc3.err; tail -3 gpurun_out/r2_bench_mlgwsc3.err; python - <<'P'
+import json
+m=json.loads(open('gpurun_out/r2_bench_mlgwsc3.json').read().strip().splitlines()[-1])
+print(m['value'], m['ms'], {k:round(v['ms'],1) for k,v in m['kernels_rank0'].items()})
+P
