@@ -16,9 +16,12 @@
 //                       d_r[k'] = E_r[k'] e^{2 pi i k' r/16000}
 //                       y[125q+r] = Re IFFT_128(d_r)[q]   (one warp per r)
 //      y is rounded to f32 exactly where the reference stores f32 audio.
-//   3. only frames 0..101 touch non-zero audio: folded 400-point real DFT per frame
-//        X_f[k] = (-1)^k u[200] + sum_{n=1..199} (e[n] cos(2 pi kn/400) - i o[n] sin(2 pi kn/400)),
-//        e/o[n] = w[n] (y~[s+n] +- y~[s+400-n]),  one warp per frame, then sparse mel + log10
+//   3. only frames 0..101 touch non-zero audio.  400-point real DFT per frame as a 200-point complex FFT of
+//        c[m] = z[2m] + i z[2m+1] (z = windowed frame), 200 = 8 x 25: 8-point DFTs in registers (one lane per n2),
+//        twiddle, 25-point DFTs with rotated twiddles (lane = (k1, k2 mod 4)), then
+//        X[k] = E[k] + e^{-2 pi i k/400} O[k], E/O = (C[k] +- conj C[200-k]) / (2, 2i); three frames per warp pass;
+//        then sparse mel + log10.  (Rounds 1-2 evaluated the folded DFT directly: 199 x 201 x 2 DFMA per frame plus
+//        the twiddle rotations, 4x the FP64 work; the FP64 pipe bounds this kernel.)
 //   4. per-sample max, clamp, affine; frames >= 102 are the per-sample constant.
 // Outputs: f32 mel-major [80,3000] (reference layout) and/or bf16 time-major [3002,80] with zero
 // pad rows (the layout the conv-stem TMA im2col wants).
@@ -38,6 +41,9 @@ struct LogmelTables {
   const double* mel_w;      // packed non-zero weights
 };
 
+#ifndef GWW_LM_DEBUG_SKIP
+#define GWW_LM_DEBUG_SKIP 0      // tuning builds only: 1 = no FFT-2048 / resampling, 2 = no 25-point DFT loop, 4 = no mel / log10
+#endif
 constexpr int kLmThreads = 384;
 constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kLmLive = 102;
@@ -81,7 +87,9 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
 
   for (long w = blockIdx.x; w < n_detwin; w += gridDim.x) {
     __syncthreads();
-    if (audio_in != nullptr) {
+    if ((GWW_LM_DEBUG_SKIP & 1) != 0) {
+      for (int i = tid; i < 16000; i += kLmThreads) y[i] = strain[w * 2048 + (i & 2047)];
+    } else if (audio_in != nullptr) {
       const float4* a4 = reinterpret_cast<const float4*>(audio_in + w * 16000L);
       for (int i = tid; i < 4000; i += kLmThreads) reinterpret_cast<float4*>(y)[i] = a4[i];
     } else {
@@ -185,77 +193,137 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
     float lmax = -10.0f;
     {
       constexpr int NF = kLmFramesPerWarp;
-      double* eo = reinterpret_cast<double*>(scratch + warp * kLmWarpScratch);  // [200][NF][2]; later pw[NF][208]
+      double2* ab = reinterpret_cast<double2*>(scratch + warp * kLmWarpScratch);   // [NF][25][8], then C [NF][200], then pw
       for (int g = warp; g < kLmLive / NF; g += kLmWarps) {
         const int f0 = g * NF;
-        double u200[NF];
-#pragma unroll
-        for (int ff = 0; ff < NF; ++ff) {
-          const int i200 = 160 * (f0 + ff);                    // base + 200, w[200] = 1, >= 0
-          u200[ff] = (i200 < 16000) ? static_cast<double>(y[i200]) : 0.0;
-        }
-        for (int idx = lane; idx < 200 * NF; idx += 32) {
-          const int nn = idx / NF, ff = idx - nn * NF;
-          if (nn >= 1) {
-            const int base = 160 * (f0 + ff) - 200;
-            const int ia = base + nn, ib = base + 400 - nn;
-            const double ya = (ia < 0) ? y[-ia] : ((ia < 16000) ? y[ia] : 0.0f);
-            const double yb = (ib < 0) ? y[-ib] : ((ib < 16000) ? y[ib] : 0.0f);
-            const double wn = 0.5 - 0.5 * tw400[nn + (nn >> 3)].x;
-            eo[(nn * NF + ff) * 2] = wn * (ya + yb);
-            eo[(nn * NF + ff) * 2 + 1] = -(wn * (ya - yb));
-          }
-        }
-        __syncwarp();
-        // twiddles by rotation in registers: t_k(n) = e^{2 pi i k n / 400} = t_k(n-1) * w_k.  (r1 fetched every
-        // t_k(n) from shared memory -- seven 16-byte loads per lane per n against 42 DFMA, and the twelve warps'
-        // loads, not the FP64 pipe, bound the kernel; the rotation costs 4 DFMA per bin instead and 199 steps of it
-        // lose ~2e-14, far below the 1e-4 gate.)
-        double re[NF][7], im[NF][7];
-        double tc[7], ts[7], wc[7], wsn[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          const int k = lane + 32 * i;
-#pragma unroll
-          for (int ff = 0; ff < NF; ++ff) {
-            re[ff][i] = (k & 1) ? -u200[ff] : u200[ff];
-            im[ff][i] = 0.0;
-          }
-          const int kk = (k < 400) ? k : 0;
-          const double2 w1 = tw400[kk + (kk >> 3)];
-          wc[i] = w1.x; wsn[i] = w1.y;
-          tc[i] = 1.0; ts[i] = 0.0;
-        }
+        // ---- step A (lanes 0..24 = n2): window, pack two real samples per complex point, 8-point DFT over n1,
+        //      twiddle e^{-2 pi i n2 k1 / 200}
+        if (lane < 25) {
 #pragma unroll 1
-        for (int nn = 1; nn < 200; ++nn) {
-          double ev[NF], ov[NF];
-          const double2* src = reinterpret_cast<const double2*>(eo + nn * NF * 2);
-#pragma unroll
           for (int ff = 0; ff < NF; ++ff) {
-            const double2 v = src[ff];                         // warp-uniform address: broadcast
-            ev[ff] = v.x;
-            ov[ff] = v.y;                                      // already negated
-          }
+            const int base = 160 * (f0 + ff) - 200;                // reflect-padded frame start
+            double vr[8], vi[8];
 #pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const double c2 = fma(tc[i], wc[i], -(ts[i] * wsn[i]));
-            ts[i] = fma(ts[i], wc[i], tc[i] * wsn[i]);
-            tc[i] = c2;
+            for (int n1 = 0; n1 < 8; ++n1) {
+              const int n = 2 * (25 * n1 + lane);
+              const int ia = base + n, ib = ia + 1;
+              const float ya = (ia < 0) ? y[-ia] : ((ia < 16000) ? y[ia] : 0.0f);
+              const float yb = (ib < 0) ? y[-ib] : ((ib < 16000) ? y[ib] : 0.0f);
+              const double wa = 0.5 - 0.5 * tw400[n + (n >> 3)].x;
+              const double wb = 0.5 - 0.5 * tw400[n + 1 + ((n + 1) >> 3)].x;
+              vr[n1] = wa * static_cast<double>(ya);
+              vi[n1] = wb * static_cast<double>(yb);
+            }
+            constexpr double kR = 0.70710678118654752440;
+            // DIF stage 1 (twiddles W8^j = 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2)
 #pragma unroll
-            for (int ff = 0; ff < NF; ++ff) {
-              re[ff][i] = fma(ev[ff], tc[i], re[ff][i]);
-              im[ff][i] = fma(ov[ff], ts[i], im[ff][i]);
+            for (int j = 0; j < 4; ++j) {
+              const double ar = vr[j] + vr[j + 4], ai = vi[j] + vi[j + 4];
+              const double br = vr[j] - vr[j + 4], bi = vi[j] - vi[j + 4];
+              vr[j] = ar; vi[j] = ai;
+              if (j == 0) { vr[4] = br; vi[4] = bi; }
+              else if (j == 1) { vr[5] = (br + bi) * kR; vi[5] = (bi - br) * kR; }
+              else if (j == 2) { vr[6] = bi; vi[6] = -br; }
+              else { vr[7] = (bi - br) * kR; vi[7] = -(br + bi) * kR; }
+            }
+            // stage 2 (W4^0 = 1, W4^1 = -i) on each half
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+              const double a0r = vr[h] + vr[h + 2], a0i = vi[h] + vi[h + 2];
+              const double b0r = vr[h] - vr[h + 2], b0i = vi[h] - vi[h + 2];
+              const double a1r = vr[h + 1] + vr[h + 3], a1i = vi[h + 1] + vi[h + 3];
+              const double b1r = vr[h + 1] - vr[h + 3], b1i = vi[h + 1] - vi[h + 3];
+              vr[h] = a0r; vi[h] = a0i; vr[h + 1] = a1r; vi[h + 1] = a1i;
+              vr[h + 2] = b0r; vi[h + 2] = b0i; vr[h + 3] = b1i; vi[h + 3] = -b1r;
+            }
+            // stage 3; position p then holds bin bitrev3(p)
+#pragma unroll
+            for (int h = 0; h < 8; h += 2) {
+              const double ar = vr[h] + vr[h + 1], ai = vi[h] + vi[h + 1];
+              const double br = vr[h] - vr[h + 1], bi = vi[h] - vi[h + 1];
+              vr[h] = ar; vi[h] = ai; vr[h + 1] = br; vi[h + 1] = bi;
+            }
+            double2* dst = ab + (ff * 25 + lane) * 8;
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const int k1 = ((pp & 1) << 2) | (pp & 2) | ((pp >> 2) & 1);
+              const int j = 2 * lane * k1;                         // e^{-2 pi i j / 400}, j <= 336
+              const double2 tw = tw400[j + (j >> 3)];
+              dst[k1] = make_double2(fma(vr[pp], tw.x, vi[pp] * tw.y), fma(vi[pp], tw.x, -(vr[pp] * tw.y)));
             }
           }
         }
-        __syncwarp();                                          // eo is dead: reuse it for the power spectra
-        double* pw = eo;                                       // [NF][208]
+        __syncwarp();
+        // ---- step C: 25-point DFTs over n2.  Lane = (k1 = lane & 7, kq = lane >> 3) owns bins k1 + 8 k2, k2 = kq + 4 i;
+        //      the twiddles e^{-2 pi i n2 k2 / 25} advance by rotation in registers (25 steps lose ~1e-15)
+        double re[NF][7], im[NF][7];
+        {
+          const int k1 = lane & 7, kq = lane >> 3;
+          double tc[7], ts[7], wc[7], wsn[7];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int k2 = kq + 4 * i;
+            const int j = (k2 < 25) ? 16 * k2 : 0;
+            const double2 w1 = tw400[j + (j >> 3)];
+            wc[i] = w1.x; wsn[i] = -w1.y;
+            tc[i] = 1.0; ts[i] = 0.0;
+#pragma unroll
+            for (int ff = 0; ff < NF; ++ff) { re[ff][i] = 0.0; im[ff][i] = 0.0; }
+          }
+#pragma unroll 1
+          for (int n2 = 0; n2 < ((GWW_LM_DEBUG_SKIP & 2) ? 1 : 25); ++n2) {
+            double2 a[NF];
+#pragma unroll
+            for (int ff = 0; ff < NF; ++ff) a[ff] = ab[(ff * 25 + n2) * 8 + k1];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+#pragma unroll
+              for (int ff = 0; ff < NF; ++ff) {
+                re[ff][i] = fma(a[ff].x, tc[i], fma(-a[ff].y, ts[i], re[ff][i]));
+                im[ff][i] = fma(a[ff].x, ts[i], fma(a[ff].y, tc[i], im[ff][i]));
+              }
+              const double c2 = fma(tc[i], wc[i], -(ts[i] * wsn[i]));
+              ts[i] = fma(ts[i], wc[i], tc[i] * wsn[i]);
+              tc[i] = c2;
+            }
+          }
+          __syncwarp();                                            // every lane has read its inputs: reuse the buffer
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int k2 = kq + 4 * i;
+            if (k2 < 25) {
+#pragma unroll
+              for (int ff = 0; ff < NF; ++ff) ab[ff * 200 + k1 + 8 * k2] = make_double2(re[ff][i], im[ff][i]);
+            }
+          }
+        }
+        __syncwarp();
+        // ---- step D: X[k] = E[k] + e^{-2 pi i k / 400} O[k] from the half-size complex transform, power spectrum
+        double pwv[NF][7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int k = lane + 32 * i;
+          const int ka = (k < 200) ? k : ((k == 200) ? 0 : 0), kb = (k == 0 || k >= 200) ? 0 : 200 - k;
+          const int kt = (k <= 200) ? k : 0;
+          const double2 tw = tw400[kt + (kt >> 3)];
+#pragma unroll
+          for (int ff = 0; ff < NF; ++ff) {
+            const double2 ck = ab[ff * 200 + ka], cm = ab[ff * 200 + kb];    // cm is conjugated below
+            const double er = 0.5 * (ck.x + cm.x), ei = 0.5 * (ck.y - cm.y);
+            const double orr = 0.5 * (ck.y + cm.y), oi = -0.5 * (ck.x - cm.x);
+            const double xr = er + fma(tw.x, orr, tw.y * oi);
+            const double xi = ei + fma(tw.x, oi, -(tw.y * orr));
+            pwv[ff][i] = xr * xr + xi * xi;
+          }
+        }
+        __syncwarp();                                          // C is dead: reuse the buffer for the power spectra
+        double* pw = reinterpret_cast<double*>(ab);            // [NF][208]
 #pragma unroll
         for (int ff = 0; ff < NF; ++ff)
 #pragma unroll
           for (int i = 0; i < 7; ++i) {
             const int k = lane + 32 * i;
-            if (k <= 200) pw[ff * 208 + k] = re[ff][i] * re[ff][i] + im[ff][i] * im[ff][i];
+            if (k <= 200) pw[ff * 208 + k] = pwv[ff][i];
           }
         __syncwarp();
 #pragma unroll 1
@@ -263,7 +331,7 @@ logmel_kernel(const float* __restrict__ strain, long n_detwin, float* __restrict
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int mm = lane + 32 * i;
-            if (mm < 80) {
+            if (mm < 80 && (GWW_LM_DEBUG_SKIP & 4) == 0) {
               const int lo = tb.mel_lo[mm], cnt = tb.mel_cnt[mm], off = tb.mel_off[mm];
               double acc = 0.0;
               for (int c = 0; c < cnt; ++c) acc = fma(tb.mel_w[off + c], pw[ff * 208 + lo + c], acc);

@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_qfront_gpu.py tests/test_mlgwsc_golden.py tests/test_train_geometry.py -m gpu -q -x -s 2>&1 | grep -v Warning | tail -15
-python bench.py --workload mlgwsc --no-cpu-baseline > gpurun_out/r2_bench_mlgwsc3.json 2> gpurun_out/r2_bench_mlgwsc3.err; tail -3 gpurun_out/r2_bench_mlgwsc3.err; python - <<'P'
-import json
-m=json.loads(open('gpurun_out/r2_bench_mlgwsc3.json').read().strip().splitlines()[-1])
-print(m['value'], m['ms'], {k:round(v['ms'],1) for k,v in m['kernels_rank0'].items()})
-P
+out=gpurun_out/r2_logmel_phases.jsonl; : > $out
+python tools/logmel_bench.py >> $out 2>&1
+for v in lm1 lm2 lm4 lm6 lm7; do GWW_LIB=gw_whisper_b200/variants/lib_$v.so python tools/logmel_bench.py >> $out 2>&1; done
+cat $out
