@@ -428,7 +428,8 @@ static void apply_fold(GemmParams& p, const LnFold& lf, int block_n) {
 
 static int run_linear(const void* A, const void* W, void* C, const float* bias, const float* resid,
                       long M, int N, int K, int epi, int block_n, cudaStream_t stream,
-                      int kind = PK_OTHER, const LnFold& lf = LnFold()) {
+                      int kind = PK_OTHER, const LnFold& lf = LnFold(), long ldc = 0) {
+  // ldc: elements between consecutive output rows (0 = N: a dense [M, N] output)
   GemmCall g{};
   g.kind = kind;
   g.a_base = A;
@@ -439,8 +440,8 @@ static int run_linear(const void* A, const void* W, void* C, const float* bias, 
   g.c_base = C;
   const bool out_f32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_GELU_POS_F32);
   const uint64_t esz = out_f32 ? 4 : 2;
-  g.c_strides[0] = (uint64_t)N * esz;
-  g.c_strides[1] = (uint64_t)M * N * esz;
+  g.c_strides[0] = (uint64_t)(ldc > 0 ? ldc : N) * esz;
+  g.c_strides[1] = (uint64_t)M * g.c_strides[0];
   g.p.rows = (int)M; g.p.batch = 1; g.p.n = N; g.p.kb_per_tap = K / 64; g.p.taps = 1; g.p.p_mod = 1;
   g.p.bias = bias; g.p.resid = resid; g.p.pos = nullptr;
   g.epi = epi;
@@ -1035,13 +1036,20 @@ static int encoder_chunk_impl(const gww_model* m, const Workspace& ws, int nc, f
       const int T = GWW_N_CTX;
       op16_t* hl = ws.h;                          // [nc, d] attention output of the last token
       op16_t* hl2 = ws.h + (size_t)nc * d;        // [nc, d] LN2 output
+      // K and V projections of all tokens into columns [d, 3d) of the qkv rows (rows d.. of the fused weight); the
+      // query projection only for the last token's row (stand-alone LayerNorm of that row, written in place)
+      const int bn_2d = pick_block_n(2 * d);
       if (fold) {
-        GWW_TRY(run_linear(ws.xb, ld.qkv_wf, qkv, ld.qkv_c2, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV,
-                           consume(ld.qkv_c1, slots_in)));
+        GWW_TRY(run_linear(ws.xb, ld.qkv_wf + (size_t)d * d, qkv + d, ld.qkv_c2 + d, nullptr, M, 2 * d, d, EPI_BIAS_BF16, bn_2d,
+                           stream, PK_GEMM_QKV, consume(ld.qkv_c1 + d, slots_in), 3L * d));
       } else {
         GWW_TRY(run_ln_t<op16_t>(ws.x, ws.h, ld.ln1_g, ld.ln1_b, M, d, 0, 1, stream));
-        GWW_TRY(run_linear(ws.h, ld.qkv_w, qkv, ld.qkv_b, nullptr, M, 3 * d, d, EPI_BIAS_BF16, bn_3d, stream, PK_GEMM_QKV));
+        GWW_TRY(run_linear(ws.h, ld.qkv_w + (size_t)d * d, qkv + d, ld.qkv_b + d, nullptr, M, 2 * d, d, EPI_BIAS_BF16, bn_2d, stream,
+                           PK_GEMM_QKV, LnFold(), 3L * d));
       }
+      GWW_TRY(run_ln_t<op16_t>(ws.x, hl2, ld.ln1_g, ld.ln1_b, nc, d, T - 1, T, stream));
+      GWW_TRY(run_linear(hl2, ld.qkv_w, qkv + (size_t)(T - 1) * 3 * d, ld.qkv_b, nullptr, nc, d, d, EPI_BIAS_BF16, bn_d, stream,
+                         PK_GEMM_QKV, LnFold(), (long)T * 3 * d));
       {
         ProfScope ps(PK_ATTN_LAST, stream);
         const size_t smem = (size_t)(((T + 3) & ~3) + 8 * 64 + 16) * sizeof(float);
