@@ -272,7 +272,7 @@ def mlgwsc_record(args, dev, rank, world, lib):
         n_dw0 = 2 * sum(p.n_windows for p in plan[0])      # det-windows rank 0 processed in the profiled pass
         # front-end kernels of rank 0's shard against the roofline that bounds each (algorithmic work per det-window,
         # QScan 8 KB in + 1 MB spectrogram out; conv1 1 MB in + 4 MB of bf16 hi/lo planes out; conv2 /
-        # conv3 604 MFLOP each -- counted once, although the split-precision path executes three MMAs per product;
+        # conv3 604 MFLOP each -- counted once, although the split-precision path executes three partial products;
         # pool 64 KB in + 480 KB of time-major features out)
         peak_tf = 1590.0
         if os.path.exists(pk_path):
@@ -282,17 +282,32 @@ def mlgwsc_record(args, dev, rank, world, lib):
                    "qadapter_conv2": ("tensor", 2.0 * 256 * 256 * 9 * 16 * 32), "qadapter_conv3": ("tensor", 2.0 * 128 * 128 * 9 * 32 * 64),
                    "qadapter_pool": ("hbm", 128 * 128 * 4 + 3002 * 80 * 2), "qadapter": ("hbm", 512 * 512 * 4 + 3002 * 80 * 2)}
         fe = {}
+        ncu_tr = {}
+        tr_path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+        if os.path.exists(tr_path):
+            ncu_tr = json.load(open(tr_path))
+
+        def fe_traffic(nm):
+            """dram read+write bytes per launch (256 det-windows) from the committed ncu --set full capture"""
+            keys = ["qscan_tiles", "qscan_interp"] if nm == "qscan" else [nm]
+            if not all(k in ncu_tr for k in keys):
+                return None
+            return sum(ncu_tr[k]["dram_bytes_per_launch"] for k in keys)
+
         for nm, (bound, work) in spec_fe.items():
             if nm not in kernels:
                 continue
             rate = work * n_dw0 / (kernels[nm]["ms"] * 1e-3)
             if bound == "hbm":
                 fe[nm] = {"bound": "hbm", "achieved": rate / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": rate / 1e9 / hbm_peak,
-                          "algorithmic_bytes_per_det_window": work, "ms": kernels[nm]["ms"], "traffic": None}
+                          "algorithmic_bytes_per_det_window": work, "ms": kernels[nm]["ms"], "traffic": fe_traffic(nm),
+                          "traffic_source": ncu_tr.get("source")}
             else:
                 fe[nm] = {"bound": "tensor", "achieved": rate / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                           "frac": rate / 1e12 / peak_tf, "algorithmic_flops_per_det_window": work, "ms": kernels[nm]["ms"],
-                          "traffic": None, "note": "bf16 hi/lo split precision: 3 MMAs per algorithmic product"}
+                          "traffic": fe_traffic(nm), "traffic_source": ncu_tr.get("source"),
+                          "note": "bf16 hi/lo split precision: two tcgen05.mma per (tap, 16-channel step) -- A_hi x [W_hi | W_lo] "
+                                  "and A_lo x W_hi -- for one algorithmic product"}
         dom = max(fe, key=lambda k: fe[k]["ms"]) if fe else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -581,9 +596,10 @@ def run_b200(args):
                 "peak_source": peak_src, "flops_per_launch": att_flops / max(att_n, 1),
                 "avg_launch_ms": att_ms / max(att_n, 1), "share_of_step": att_ms / max(sum(ms_k), 1e-9),
                 "note": "head_dim 64: one exp per 128 MAC, so the softmax (MUFU.EX2 16/clk/SM) needs >= 2x the tensor time "
-                        "of a tile: the tensor-pipe ceiling of this kernel is ~45% of peak (profiles/r2_ubench_softmax_mix2.txt: "
+                        "of a tile: the tensor-pipe ceiling of this kernel is ~50% of peak (profiles/r2_ubench_softmax_mix2.txt: "
                         "12.6 exp/clk/SM is the instruction-mix ceiling at two softmax warps per sub-partition, 15.1 with 2 of 8 "
-                        "pairs on the FMA-pipe polynomial, which the kernel uses since round 2)"}
+                        "pairs on the FMA-pipe polynomial, which the kernel uses; r2 ncu: XU 64 %, tensor 42 % active, "
+                        "profiles/r2_ncu_summary.csv)"}
     if "logmel" in kernels:
         lm_bytes = (2048 * 4 + 3002 * 80 * 2) * n_dw   # fused path writes bf16 time-major features
         kernels["logmel"]["gbs"] = lm_bytes / (kernels["logmel"]["ms_per_step"] * 1e-3) / 1e9

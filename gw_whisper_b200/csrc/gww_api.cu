@@ -494,6 +494,16 @@ static bool attention_persistent() {
   return v != 0;
 }
 
+// persistent TMA-fed conv1 of the Q-Adapter (default) vs one CTA per tile with plain loads (GWW_QA_CONV1_TMA=0)
+static bool qadapter_conv1_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GWW_QA_CONV1_TMA");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int run_attention(const void* qkv, void* out, long n, int T, int d, cudaStream_t stream) {
   if (d % 64 != 0) return fail(GWW_ERR_INVALID, "attention: d_model %% 64 != 0");
   CUtensorMap tmQ, tmO;
@@ -1619,7 +1629,17 @@ static int run_qadapter(const gww_qfront* qf, const float* spec, long n, int det
     LAUNCH_CHECK();
   } else if (qadapter_tc_enabled() && F % 64 == 0 && T % 32 == 0) {
     // tensor-core path: conv1 (CUDA cores, fp32) writes bf16 hi/lo planes; conv2 / conv3 are tcgen05 implicit GEMMs
-    {
+    if (qadapter_conv1_tma_enabled()) {
+      CUtensorMap tm1;
+      const uint64_t d1[3] = {(uint64_t)T, (uint64_t)F, (uint64_t)n};
+      const uint64_t s1[2] = {(uint64_t)T * 4, (uint64_t)T * F * 4};
+      const uint32_t b1[3] = {kC1Pitch, 34, 1};
+      GWW_TRY(make_map(&tm1, true, 3, spec, d1, s1, b1, false));
+      const long tiles1 = (long)(F / 32) * (T / 32) * n;
+      const int grid1 = (int)std::min<long>(4L * g_num_sms, tiles1);
+      ProfScope ps(PK_QA_CONV1, s);
+      qadapter_conv1_tma_kernel<<<grid1, 256, 0, s>>>(tm1, ws.act1, F, T, n, qf->ad);
+    } else {
       ProfScope ps(PK_QA_CONV1, s);
       qadapter_conv1_kernel<true><<<dim3(T / 32, F / 32, (unsigned)n), 256, 0, s>>>(spec, ws.act1, F, T, qf->ad);
     }

@@ -499,6 +499,113 @@ qadapter_conv1_kernel(const float* __restrict__ spec, float* __restrict__ act1, 
   }
 }
 
+// The same convolution for the tensor-core path, persistent and TMA-fed: r2 ncu of qadapter_conv1_kernel<true> showed
+// 37 % of the warp samples waiting on the global loads of the next 34 x 34 input tile (long scoreboard) although four
+// CTAs per SM overlap.  Here CTAs loop over tiles; one thread fetches the NEXT tile with a single TMA box
+// ({40, 34} floats starting 4 columns left of the tile: 16-byte aligned rows; out-of-image coordinates are zero-filled = the padding) into the other half
+// of a double buffer while the 256 threads compute the current one.  Arithmetic and its order are those of
+// qadapter_conv1_kernel<true>: bit-identical outputs.
+constexpr int kC1Pitch = 40;   // staged row: image columns 32 bx - 4 .. 32 bx + 35 (the TMA start must be 16-byte aligned)
+__global__ void __launch_bounds__(256, 4)
+qadapter_conv1_tma_kernel(const __grid_constant__ CUtensorMap tmSpec,   // {W, H, n} f32, box {40, 34, 1}
+                          float* __restrict__ act1, int H, int W, long n_img, const QAdapterDev ad) {
+  __shared__ __align__(128) float tile[2][1376];      // 34 rows x 40 floats, padded to a 128-byte multiple (TMA destination)
+  __shared__ __align__(16) float ws[9 * 16 + 16];
+  __shared__ __align__(8) uint64_t full[2];
+  for (int i = threadIdx.x; i < 9 * 16; i += 256) ws[i] = ad.w1[i];
+  if (threadIdx.x < 16) ws[144 + threadIdx.x] = ad.b1[threadIdx.x];
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmSpec);
+    mbar_init(smem_u32(&full[0]), 1);
+    mbar_init(smem_u32(&full[1]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int tiles_x = W >> 5, tiles_y = H >> 5;
+  const long tiles_per_img = static_cast<long>(tiles_x) * tiles_y;
+  const long n_tiles = tiles_per_img * n_img;
+  auto stage = [&](long t, int b) {                 // one thread
+    const long img = t / tiles_per_img;
+    const int rem = static_cast<int>(t - img * tiles_per_img);
+    const int by = rem / tiles_x, bx = rem - by * tiles_x;
+    mbar_arrive_expect_tx(smem_u32(&full[b]), 34 * kC1Pitch * 4);
+    tma_load_3d(smem_u32(&tile[b][0]), &tmSpec, smem_u32(&full[b]), 32 * bx - 4, 32 * by - 1, static_cast<int>(img));
+  };
+  const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+  const int PH = H >> 1, PW = W >> 1;
+  long t = blockIdx.x;
+  if (t < n_tiles && threadIdx.x == 0) stage(t, 0);
+  for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    const int b = it & 1;
+    __syncthreads();                                 // every thread is done with the other buffer (tile it - 1)
+    if (threadIdx.x == 0 && t + gridDim.x < n_tiles) stage(t + gridDim.x, b ^ 1);
+    mbar_wait(smem_u32(&full[b]), (it >> 1) & 1);
+    float p[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float* row = &tile[b][(2 * ly + a) * kC1Pitch + 2 * lx + 3];
+      p[a][0] = row[0]; p[a][1] = row[1]; p[a][2] = row[2]; p[a][3] = row[3];
+    }
+    float o[16];
+#pragma unroll
+    for (int hc = 0; hc < 2; ++hc) {
+      uint64_t acc[4][4];
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        const uint64_t bv = f2_pack(ws[144 + 8 * hc + 2 * cp], ws[144 + 8 * hc + 2 * cp + 1]);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) acc[px][cp] = bv;
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          uint64_t w2[4];
+#pragma unroll
+          for (int c4 = 0; c4 < 2; ++c4) {
+            const float4 wv = *reinterpret_cast<const float4*>(&ws[(ky * 3 + kx) * 16 + 8 * hc + 4 * c4]);
+            w2[2 * c4] = f2_pack(wv.x, wv.y);
+            w2[2 * c4 + 1] = f2_pack(wv.z, wv.w);
+          }
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const float iv = p[dy + ky][dx + kx];
+              const uint64_t iv2 = f2_pack(iv, iv);
+#pragma unroll
+              for (int cp = 0; cp < 4; ++cp) acc[dy * 2 + dx][cp] = f2_fma(iv2, w2[cp], acc[dy * 2 + dx][cp]);
+            }
+        }
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        float b0 = 0.f, b1 = 0.f;     // ReLU floor: max(relu(a), relu(b), ...) == max(0, a, b, ...)
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          float a0, a1;
+          f2_unpack(acc[px][cp], a0, a1);
+          b0 = fmaxf(b0, a0);
+          b1 = fmaxf(b1, a1);
+        }
+        o[8 * hc + 2 * cp] = b0;
+        o[8 * hc + 2 * cp + 1] = b1;
+      }
+    }
+    const long img = t / tiles_per_img;
+    const int rem = static_cast<int>(t - img * tiles_per_img);
+    const int py0 = (rem / tiles_x) * 16, px0 = (rem % tiles_x) * 16;
+    uint4* dst = reinterpret_cast<uint4*>(act1) + img * 4L * PH * PW + static_cast<long>(py0 + ly) * PW + (px0 + lx);
+#pragma unroll
+    for (int hc = 0; hc < 2; ++hc) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_bf16x2(o[8 * hc + 2 * e], o[8 * hc + 2 * e + 1], hi[e], lo[e]);
+      dst[static_cast<long>(hc) * PH * PW] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      dst[static_cast<long>(2 + hc) * PH * PW] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // conv3x3(16->32, pad 1) + ReLU + maxpool2 : act1 [n,H,W,16] -> act2 [n,H/2,W/2,32]
 // CTA = 16x16 conv pixels (8x8 pooled) x 32 output channels.  Thread = (2x2 pixel quad, 8 channels):
 // 32 accumulators; input tile in smem channel-major [16][18][24] (pitch 24 makes the float2 loads of a

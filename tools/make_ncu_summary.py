@@ -64,6 +64,13 @@ for cap in ("attn", "logmel", "gemm", "qfront"):
         if cap == "attn":
             rec["role"] = "attention"
             traffic["attention_persist_kernel"] = {"dram_bytes_per_launch": rec["dram_bytes"], "det_windows": 256}
+        if cap == "qfront":
+            k = rec["kernel"]
+            role = ("qscan_tiles" if k.startswith("qscan_tiles") else "qscan_interp" if k.startswith("qscan_interp") else
+                    "qadapter_conv1" if k.startswith("qadapter_conv1") else "qadapter_pool" if k.startswith("qadapter_pool") else
+                    "qadapter_conv2" if "<16, 32" in k else "qadapter_conv3" if "<32, 64" in k else k)
+            rec["role"] = role
+            traffic[role] = {"dram_bytes_per_launch": rec["dram_bytes"], "det_windows": 256}
         if cap == "logmel":
             rec["role"] = "logmel"
             traffic["logmel_kernel"] = {"dram_bytes_per_launch": rec["dram_bytes"], "det_windows": 256}
