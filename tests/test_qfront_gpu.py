@@ -140,14 +140,17 @@ def test_qadapter_fp32_cuda_core_path_still_matches(tmp_path):
         "a = QTransformAdapter(n_detectors=2); a.load_state_dict(torch.load(sys.argv[1]))\n"
         "torch.save(a.adapt(torch.load(sys.argv[2]).cuda(), 1).cpu(), sys.argv[3])\n")
     outs = {}
-    for tc in ("0", "1"):
+    for tc, env in (("0", {"GWW_QADAPTER_TC": "0"}), ("1", {"GWW_QADAPTER_TC": "1"}),
+                    ("1-conv1-plain", {"GWW_QADAPTER_TC": "1", "GWW_QA_CONV1_TMA": "0"})):
         out = str(tmp_path / f"out{tc}.pt")
         subprocess.run([sys.executable, "-c", code, sd, str(tmp_path / "spec.pt"), out], check=True,
-                       env={**os.environ, "GWW_QADAPTER_TC": tc}, timeout=600)
+                       env={**os.environ, **env}, timeout=600)
         outs[tc] = torch.load(out)
     e0, e1, e01 = _nerr(outs["0"], want), _nerr(outs["1"], want), _nerr(outs["1"], outs["0"])
     print(f"adapter CNN vs oracle: fp32 CUDA-core path {e0:.3e}, tensor-core path {e1:.3e}; between them {e01:.3e}")
     assert e0 <= 5e-6 and e1 <= 4e-5 and e01 <= 4e-5
+    # the persistent TMA-fed conv1 (default) and the one-CTA-per-tile conv1 run the same arithmetic in the same order
+    assert torch.equal(outs["1"], outs["1-conv1-plain"])
 
 
 def _reference_model(base, dora, adapter, num_classes=2, use_last_token=True):
