@@ -56,6 +56,9 @@ struct QPlan {
   const QRow* orig;        // rows in plane / frequency order (for interpolation)
 };
 
+#ifndef GWW_QS_DEBUG_SKIP
+#define GWW_QS_DEBUG_SKIP 0     // tuning builds only: 1 = no median (warp rows), 2 = no median (CTA rows), 4 = no CTA rows, 8 = no warp rows
+#endif
 constexpr int kQsThreads = 512;
 constexpr int kQsWarps = kQsThreads / 32;
 constexpr int kQsWarpScratch = 2 * 512;                       // float2 elements per warp (ping-pong)
@@ -90,17 +93,33 @@ __device__ __forceinline__ float2* fft_stockham(float2* a, float2* b, int n, int
   return a;
 }
 
-// k-th smallest (1-based) of non-negative floats by bisection on the bit pattern; `count_le(v)` must
-// return, to every participating thread, the number of elements whose bits are <= v.
-template <typename CountFn>
-__device__ __forceinline__ uint32_t kth_smallest_bits(int k, CountFn count_le) {
-  uint32_t lo = 0u, hi = 0x7f800000u;     // energies are finite and >= 0
-#pragma unroll 1
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (count_le(mid) >= k) hi = mid; else lo = mid + 1;
+// Radix select, one 8-bit digit per pass (4 passes for non-negative floats compared as uint32): the bin of a 256-entry
+// histogram in which the cumulative count first reaches k (1-based), and the count in the bins below it.  Executed by
+// every lane of a warp (lane l holds bins 8l .. 8l+7); the result is warp-uniform.  (Rounds 1-2 bisected on the bit
+// pattern: 31 count-and-reduce rounds per row -- with one __syncthreads each for the CTA-level rows -- which the r2
+// ablation put at 34 % of the whole QScan front end, tools/qscan_bench.py.)
+__device__ __forceinline__ void radix_pick_bin(const int* __restrict__ hist, int k, int lane, int& bin, int& below) {
+  int c[8], s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; s += c[j]; }
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
-  return lo;
+  const int excl = incl - s;
+  const bool mine = (excl < k) && (k <= incl);                 // exactly one lane (k <= total)
+  int b = 0, bl = excl;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (bl + c[j] < k && j < 7) { bl += c[j]; b = j + 1; }
+    else break;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  const int src = __ffs(m) - 1;
+  bin = __shfl_sync(0xffffffffu, lane * 8 + b, src);
+  below = __shfl_sync(0xffffffffu, bl, src);
 }
 
 __global__ void __launch_bounds__(kQsThreads, 1)
@@ -147,7 +166,7 @@ qscan_tiles_kernel(const float* __restrict__ strain, long n_detwin, long win_str
       int ri = 0;
       if (lane == 0) ri = atomicAdd(&ctr[0], 1);
       ri = __shfl_sync(0xffffffffu, ri, 0);
-      if (ri >= pl.n_rows_warp) break;
+      if (ri >= pl.n_rows_warp || (GWW_QS_DEBUG_SKIP & 8)) break;
       const QRow row = pl.rows[ri];
       const int n = row.n;
       for (int k = lane; k < n; k += 32) {
@@ -177,16 +196,36 @@ qscan_tiles_kernel(const float* __restrict__ strain, long n_detwin, long win_str
           e[i] = 0.f;
         }
       }
-      auto count_le = [&](uint32_t v) {
-        int c = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) c += (i < per && __float_as_uint(e[i]) <= v) ? 1 : 0;
-        return __reduce_add_sync(0xffffffffu, c);
-      };
       const int k1 = n >> 1;                                 // sorted[n/2 - 1] (0-based) is the k1-th smallest
-      const uint32_t lo_bits = kth_smallest_bits(k1, count_le);
+      // radix select over the row's n energies; the FFT buffers are dead (energies are in registers): histogram there
+      int* hist = reinterpret_cast<int*>(a);
+      uint32_t lo_bits = 0u;
+      int kk = k1, n_le = 0;
+      __syncwarp();
+#pragma unroll 1
+      for (int pass = 0; pass < 4 && !(GWW_QS_DEBUG_SKIP & 1); ++pass) {
+        const int shift = 24 - 8 * pass;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i < per) {
+            const uint32_t v = __float_as_uint(e[i]);
+            if (pass == 0 || (v >> (shift + 8)) == (lo_bits >> (shift + 8))) atomicAdd(&hist[(v >> shift) & 255u], 1);
+          }
+        }
+        __syncwarp();
+        int bin, below;
+        radix_pick_bin(hist, kk, lane, bin, below);
+        if (pass == 3) n_le = (k1 - kk) + below + hist[bin];   // elements <= the selected value
+        kk -= below;
+        lo_bits |= static_cast<uint32_t>(bin) << shift;
+        __syncwarp();
+      }
+      if (GWW_QS_DEBUG_SKIP & 1) { lo_bits = 0x3f800000u; n_le = n; }
       uint32_t hi_bits = lo_bits;
-      if (count_le(lo_bits) < k1 + 1) {                      // next distinct value above
+      if (n_le < k1 + 1) {                                   // next distinct value above
         uint32_t mn = 0x7f800000u;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -215,7 +254,7 @@ qscan_tiles_kernel(const float* __restrict__ strain, long n_detwin, long win_str
   {
     float2* a = scratch;
     float2* b = scratch + 2048;
-    for (int ri = pl.n_rows_warp; ri < pl.n_rows; ++ri) {
+    for (int ri = pl.n_rows_warp; ri < ((GWW_QS_DEBUG_SKIP & 4) ? 0 : pl.n_rows); ++ri) {
       const QRow row = pl.rows[ri];
       const int n = row.n;
       for (int k = tid; k < n; k += kQsThreads) {
@@ -245,29 +284,35 @@ qscan_tiles_kernel(const float* __restrict__ strain, long n_detwin, long win_str
         }
       }
       __syncthreads();                                       // r (== a or b) is dead: next row may overwrite it
-      // block-wide count with ONE barrier per query: three rotating counters; counter (q+1)%3 is
-      // cleared by thread 0 before the barrier of query q (its last readers passed barrier q-1).
-      int qn = 0;
-      auto count_le = [&](uint32_t v) {
-        int c = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c += (i < per && __float_as_uint(e[i]) <= v) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        int* slot = cnt_s + qn;
-        const int nxt = (qn == 2) ? 0 : qn + 1;
-        if (tid == 0) cnt_s[nxt] = 0;
-        if (lane == 0 && c) atomicAdd(slot, c);
-        __syncthreads();
-        qn = nxt;
-        return *slot;
-      };
-      if (tid == 0) { cnt_s[0] = 0; cnt_s[1] = 0; cnt_s[2] = 0; }
+      // block-wide radix select: four 256-bin histograms (one per pass, cleared together) in the dead FFT buffer; one
+      // barrier per pass, every warp scans the histogram for itself
+      int* hist = reinterpret_cast<int*>(scratch);           // [4][256]
+      for (int i = tid; i < 4 * 256; i += kQsThreads) hist[i] = 0;
       __syncthreads();
       const int k1 = n >> 1;
-      const uint32_t lo_bits = kth_smallest_bits(k1, count_le);
+      uint32_t lo_bits = 0u;
+      int kk = k1, n_le = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 4 && !(GWW_QS_DEBUG_SKIP & 2); ++pass) {
+        const int shift = 24 - 8 * pass;
+        int* h = hist + 256 * pass;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < per) {
+            const uint32_t v = __float_as_uint(e[i]);
+            if (pass == 0 || (v >> (shift + 8)) == (lo_bits >> (shift + 8))) atomicAdd(&h[(v >> shift) & 255u], 1);
+          }
+        }
+        __syncthreads();
+        int bin, below;
+        radix_pick_bin(h, kk, lane, bin, below);
+        if (pass == 3) n_le = (k1 - kk) + below + h[bin];
+        kk -= below;
+        lo_bits |= static_cast<uint32_t>(bin) << shift;
+      }
+      if (GWW_QS_DEBUG_SKIP & 2) { lo_bits = 0x3f800000u; n_le = n; }
       uint32_t hi_bits = lo_bits;
-      const int c_le = count_le(lo_bits);
-      if (c_le < k1 + 1) {
+      if (n_le < k1 + 1) {
         uint32_t mn = 0x7f800000u;
 #pragma unroll
         for (int i = 0; i < 4; ++i)

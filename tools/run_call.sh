@@ -1,12 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-N=4
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err
-tail -3 gpurun_out/r2_bench_${N}gpu.err
-python - <<'P'
+timeout 900 python -m pytest tests/test_qfront_gpu.py tests/test_mlgwsc_golden.py -m gpu -q -x -s 2>&1 | grep -v Warning | grep "qscan\|QScan\|tiles\|spectrogram\|passed\|failed\|Error" | head
+python tools/qscan_bench.py 2>&1 | tail -1
+python bench.py --workload mlgwsc --no-cpu-baseline > gpurun_out/r2_bench_mlgwsc5.json 2> gpurun_out/r2_bench_mlgwsc5.err; tail -3 gpurun_out/r2_bench_mlgwsc5.err; python - <<'P'
 import json
-d=json.loads(open('gpurun_out/r2_bench_4gpu.json').read().strip().splitlines()[-1])
-print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
-m=d['mlgwsc']; print(m['n_gpus'], m['value'], m['ms'], m['triggers'], m['triggers_per_rank'], m['prefix_check'])
+m=json.loads(open('gpurun_out/r2_bench_mlgwsc5.json').read().strip().splitlines()[-1])
+print(m['value'], m['ms'], m['triggers'], {k:round(v['ms'],1) for k,v in m['kernels_rank0'].items()})
 P
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 1 --warmup 0 2> gpurun_out/r2_ref_${N}gpu.err | cut -c1-200
