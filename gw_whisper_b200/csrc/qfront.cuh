@@ -384,10 +384,18 @@ qscan_interp_kernel(const float* __restrict__ tiles, const unsigned int* __restr
   const int R = pl.plane_nrows[plane];
   const QRow* rows = pl.orig + pl.plane_row0[plane];
   const float* src = tiles + w * static_cast<long>(pl.n_tiles);
-  // ---- time axis: every row -> out_t samples
-  for (int idx = threadIdx.x; idx < R * out_t; idx += kQiThreads) {
-    const int r = idx / out_t, t = idx - r * out_t;
-    const QRow row = rows[r];
+  // ---- this CTA's slice of the output frequency axis and the rows of the plane its 4-tap stencils touch
+  const int f_per = (out_f + kQiSplit - 1) / kQiSplit;
+  const int f0 = blockIdx.y * f_per;
+  const int f1 = min(out_f, f0 + f_per);
+  const float scale_f = static_cast<float>(R) / static_cast<float>(out_f);
+  const int r_lo = max(0, static_cast<int>(floorf(scale_f * (static_cast<float>(f0) + 0.5f) - 0.5f)) - 1);
+  const int r_hi = min(R - 1, static_cast<int>(floorf(scale_f * (static_cast<float>(f1 - 1) + 0.5f) - 0.5f)) + 2);
+  const int n_r = (f1 > f0) ? r_hi - r_lo + 1 : 0;
+  // ---- time axis: those rows -> out_t samples (rounds 1-2: every CTA interpolated all R rows, 4x the work)
+  for (int idx = threadIdx.x; idx < n_r * out_t; idx += kQiThreads) {
+    const int rl = idx / out_t, t = idx - rl * out_t;
+    const QRow row = rows[r_lo + rl];
     const float scale = static_cast<float>(row.n) / static_cast<float>(out_t);
     const float s = scale * (static_cast<float>(t) + 0.5f) - 0.5f;
     const float fl = floorf(s);
@@ -405,10 +413,6 @@ qscan_interp_kernel(const float* __restrict__ tiles, const unsigned int* __restr
   }
   __syncthreads();
   // ---- frequency axis
-  const int f_per = (out_f + kQiSplit - 1) / kQiSplit;
-  const int f0 = blockIdx.y * f_per;
-  const int f1 = min(out_f, f0 + f_per);
-  const float scale_f = static_cast<float>(R) / static_cast<float>(out_f);
   float* dst = spec + w * static_cast<long>(out_f) * out_t;
   for (int fo = f0; fo < f1; ++fo) {
     const float s = scale_f * (static_cast<float>(fo) + 0.5f) - 0.5f;
@@ -418,7 +422,7 @@ qscan_interp_kernel(const float* __restrict__ tiles, const unsigned int* __restr
     cubic_coeffs(s - fl, c);
     int rr[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) rr[k] = min(max(iy - 1 + k, 0), R - 1);
+    for (int k = 0; k < 4; ++k) rr[k] = min(max(iy - 1 + k, 0), R - 1) - r_lo;   // clamped rows stay inside [r_lo, r_hi]
     for (int t = threadIdx.x; t < out_t; t += kQiThreads) {
       float acc = 0.f;
 #pragma unroll
