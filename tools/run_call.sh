@@ -1,11 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-N=8
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err
-tail -3 gpurun_out/r2_bench_${N}gpu.err
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/r2_bench_8gpu.json').read().strip().splitlines()[-1])
-print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
-m=d['mlgwsc']; print(m['n_gpus'], m['value'], m['ms'], m['triggers'], m['triggers_per_rank'], m['prefix_check'])
-P
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k attention 2>&1 | tail -3
+out=gpurun_out/r2_attn_defer.jsonl; : > $out
+python tools/attn_bench.py --reps 20 >> $out 2>gpurun_out/r2_attn_mw.err
+GWW_LIB=gw_whisper_b200/variants/lib_de0.so timeout 120 python tools/attn_bench.py --reps 20 >> $out 2>>gpurun_out/r2_attn_mw.err
+python tools/attn_bench.py --reps 20 >> $out 2>gpurun_out/r2_attn_mw.err
+GWW_LIB=gw_whisper_b200/variants/lib_de0.so timeout 120 python tools/attn_bench.py --reps 20 >> $out 2>>gpurun_out/r2_attn_mw.err
+python tools/attn_bench.py --reps 20 --d 384 >> $out 2>>gpurun_out/r2_attn_mw.err
+cat $out
+GWW_LIB=gw_whisper_b200/variants/lib_de1tr.so timeout 120 python tools/attn_bench.py --reps 1 --warmup 0 --det-windows 74 2>&1 | grep "gww-" | cut -c1-360 | sort | head -8
