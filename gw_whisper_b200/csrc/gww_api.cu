@@ -341,6 +341,9 @@ static int gemm_pair_mode(const GemmParams& p, int epi, int ktot) {
   const int tiles_m = ((p.rows + 127) / 128) * p.batch;
   if (tiles_m < g_num_sms) return 1;
   if (epi == EPI_BIAS_GELU_BF16) return 1;
+  // whisper-tiny's qkv projection (K = 384: six k-blocks per tile): measured inside the MLGWSC-1 search, single CTA
+  // 400 ms per hour of strain against 492 for the pair (r2); fc2 / conv2 / fc1 of the same model are best as chosen below
+  if (epi == EPI_BIAS_BF16 && ktot <= 384) return 1;
   if (epi == EPI_BIAS_RESID_F32 && ktot <= 768 && p.n <= 768) return 1;
   return 2;
 }
