@@ -331,7 +331,22 @@ static int launch_gemm_bn(int epi, const CUtensorMap& a, const CUtensorMap& b, c
 // out_proj 17.7 / 16.3 and fc1 (GELU epilogue) 32.4 / 30.9 -- the small-N K=512 residual GEMM is HBM-bound
 // and the GELU GEMM is bound by its epilogue's issue slots, where the pair's lock-step costs more than
 // its halved operand traffic saves.
-static int gemm_pair_mode(const GemmParams& p, int epi, int ktot) {
+static int gemm_pair_mode(const GemmParams& p, int epi, int ktot, int kind) {
+  // tuning override per GEMM kind: GWW_GEMM_MC_QKV / _O / _FC1 / _FC2 / _CONV1 / _CONV2 = 1 | 2 (read once)
+  static int per_kind[PK_COUNT];
+  static bool per_kind_init = false;
+  if (!per_kind_init) {
+    const struct { int k; const char* name; } tbl[] = {{PK_GEMM_QKV, "GWW_GEMM_MC_QKV"}, {PK_GEMM_O, "GWW_GEMM_MC_O"},
+                                                       {PK_GEMM_FC1, "GWW_GEMM_MC_FC1"}, {PK_GEMM_FC2, "GWW_GEMM_MC_FC2"},
+                                                       {PK_GEMM_CONV1, "GWW_GEMM_MC_CONV1"}, {PK_GEMM_CONV2, "GWW_GEMM_MC_CONV2"}};
+    for (int i = 0; i < PK_COUNT; ++i) per_kind[i] = 0;
+    for (const auto& e : tbl) { const char* v = getenv(e.name); per_kind[e.k] = v ? atoi(v) : 0; }
+    per_kind_init = true;
+  }
+  if (kind >= 0 && kind < PK_COUNT && (per_kind[kind] == 1 || per_kind[kind] == 2)) {
+    const int tiles_m_k = ((p.rows + 127) / 128) * p.batch;
+    return (per_kind[kind] == 2 && tiles_m_k < 2) ? 1 : per_kind[kind];
+  }
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("GWW_GEMM_MC");
@@ -359,7 +374,7 @@ static int run_gemm(const GemmCall& g, cudaStream_t stream) {
   GWW_TRY(make_map(&tmA, false, 4, g.a_base, g.a_dims, g.a_strides, abox));
   const uint64_t wdims[2] = {(uint64_t)g.ktot, (uint64_t)g.p.n};
   const uint64_t wstr[1] = {(uint64_t)g.ktot * 2};
-  const int mc = gemm_pair_mode(g.p, g.epi, g.ktot);
+  const int mc = gemm_pair_mode(g.p, g.epi, g.ktot, g.kind);
   const uint32_t wbox[2] = {64, (uint32_t)(g.block_n / mc)};
   GWW_TRY(make_map(&tmB, false, 2, g.w_base, wdims, wstr, wbox));
   GemmParams p = g.p;
@@ -997,7 +1012,8 @@ static int encoder_chunk_impl(const gww_model* m, const Workspace& ws, int nc, f
   const int bn_d = pick_block_n(d), bn_3d = pick_block_n(3 * d), bn_f = pick_block_n(f);
   // out_proj (K = N = d) is HBM-bound (10 d bytes per row against 2 d^2 FLOP): a 128-wide N tile leaves room
   // for more operand stages in flight and measured 0.355 vs 0.449 ms (whisper-base, 384k rows; 5.5 TB/s)
-  const int bn_o = (d % 128 == 0) ? 128 : bn_d;
+  static const int bn_o_env = getenv("GWW_GEMM_BN_O") ? atoi(getenv("GWW_GEMM_BN_O")) : 0;   // tuning override
+  const int bn_o = (bn_o_env == 128 || bn_o_env == 192 || bn_o_env == 256) ? bn_o_env : ((d % 128 == 0) ? 128 : bn_d);
   // producer side of a residual GEMM / consumer side of the Linear after a LayerNorm
   auto produce = [&]() { LnFold lf; if (fold) { lf.xb = ws.xb; lf.stats_out = ws.stats; lf.d_model = d; } return lf; };
   auto consume = [&](const float* c1, int slots) {
