@@ -23,10 +23,11 @@
 //     nine descriptors into the same staged tile; zero padding comes from the staging loads.
 //   * weights live in shared memory in the same canonical layout ([tap][plane][Cout] x 16 B, hi and lo).
 //   * one persistent CTA per SM made of G independent 128-thread groups (named barriers): each group runs a
-//     software pipeline over its tiles with two staging buffers -- cp.async of tile t+2 in flight, tile t+1 resident,
-//     27 / 54 MMAs of tile t issued by one elected thread -> tcgen05.commit -> tcgen05.ld -> epilogue of tile t
-//     overlapping the MMAs of tile t+1 -- and the groups interleave on the tensor pipe.  Activations move between the kernels in the plane format (bf16 hi/lo): act1 4 planes of 256x256,
-//     act2 8 planes of 128x128 -- the same bytes as the fp32 NHWC tensors of round 1.
+//     software pipeline over its tiles with two staging buffers -- the TMA box of tile t+2 in flight, tile t+1
+//     resident, 18 / 36 MMAs of tile t issued by one elected thread -> tcgen05.commit -> tcgen05.ld -> epilogue of
+//     tile t overlapping the MMAs of tile t+1 -- and the groups interleave on the tensor pipe.  Activations move
+//     between the kernels in the plane format (bf16 hi/lo): act1 4 planes of 256x256, act2 8 planes of 128x128 --
+//     the same bytes as the fp32 NHWC tensors of round 1.
 //   * epilogues: conv2 = 2x2 max-pool by warp shuffles (the 16x8 tile maps pool partners to lanes ^1 and ^8),
 //     bias, ReLU, hi/lo split, 16-byte plane stores; conv3 = bias, ReLU, the 1x1 conv (64 -> 1) as a dot product.
 #pragma once
@@ -69,12 +70,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
