@@ -85,30 +85,47 @@ last_row_attention_kernel(const op16_t* __restrict__ qkv, op16_t* __restrict__ o
   const int h = blockIdx.x;
   const long b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const op16_t* base = qkv + b * static_cast<long>(T) * 3 * d + h * 64 + 2 * lane;
-  const float2 q = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(base + static_cast<long>(T - 1) * 3 * d));
-  const op16_t* kb = base + d;
+  const op16_t* head0 = qkv + b * static_cast<long>(T) * 3 * d + h * 64;          // q of token 0, this head
+  const op16_t* base = head0 + 2 * lane;
   const op16_t* vb = base + 2 * d;
-  float wmax = -INFINITY;
-  for (int k0 = warp * 4; k0 < T; k0 += 32) {        // 4 keys per warp iteration: 4 loads in flight
-    float dot[4];
+  // scores: one thread per key (its 128-byte K row against the query row held in registers); r1 spread each key over the
+  // 32 lanes and paid five shuffle rounds per dot product
+  float q[64];
+  {
+    const uint4* qr = reinterpret_cast<const uint4*>(head0 + static_cast<long>(T - 1) * 3 * d);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = min(k0 + u, T - 1);
-      const float2 kv = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(kb + static_cast<long>(k) * 3 * d));
-      dot[u] = q.x * kv.x + q.y * kv.y;
-    }
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = qr[c];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (k0 + u < T) {
-        if (lane == 0) sc[k0 + u] = dot[u];
-        wmax = fmaxf(wmax, dot[u]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(&w[e]));
+        q[8 * c + 2 * e] = f.x;
+        q[8 * c + 2 * e + 1] = f.y;
       }
+    }
   }
+  float wmax = -INFINITY;
+  for (int k = threadIdx.x; k < T; k += 256) {
+    const uint4* kr = reinterpret_cast<const uint4*>(head0 + d + static_cast<long>(k) * 3 * d);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = kr[c];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = op16x2_to_float2(*reinterpret_cast<const op16x2_t*>(&w[e]));
+        d0 = fmaf(q[8 * c + 2 * e], f.x, d0);
+        d1 = fmaf(q[8 * c + 2 * e + 1], f.y, d1);
+      }
+    }
+    const float dot = d0 + d1;
+    sc[k] = dot;
+    wmax = fmaxf(wmax, dot);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
   if (lane == 0) red[warp] = wmax;
   __syncthreads();
   float m = red[0];
