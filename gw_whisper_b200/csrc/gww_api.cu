@@ -682,6 +682,7 @@ struct LayerDev {
 struct gww_model {
   gww_encoder_config_t cfg;
   op16_t *conv1_w, *conv2_w;   // [d, 384], [d, 3d]
+  op16_t* conv1_wp = nullptr;  // [d, 256]: the three taps' 80 channels contiguous (k = 80 tap + c), zero-padded
   float *conv1_b, *conv2_b, *pos_emb, *lnp_g, *lnp_b;
   std::vector<LayerDev> layers;
   std::vector<void*> owned;
@@ -775,6 +776,11 @@ extern "C" int gww_model_create(const gww_encoder_config_t* cfg, const gww_encod
       for (int ci = 0; ci < 80; ++ci)
         for (int t = 0; t < 3; ++t) p[(size_t)co * 384 + t * 128 + ci] = w->conv1_w[((size_t)co * 80 + ci) * 3 + t];
     guard(dev_bf16(m, p, &m->conv1_w));
+    std::vector<float> pp((size_t)d * 256, 0.f);
+    for (int co = 0; co < d; ++co)
+      for (int ci = 0; ci < 80; ++ci)
+        for (int t = 0; t < 3; ++t) pp[(size_t)co * 256 + t * 80 + ci] = w->conv1_w[((size_t)co * 80 + ci) * 3 + t];
+    guard(dev_bf16(m, pp, &m->conv1_wp));
     std::vector<float> p2((size_t)d * 3 * d);
     for (int co = 0; co < d; ++co)
       for (int ci = 0; ci < d; ++ci)
@@ -1027,12 +1033,25 @@ static int encoder_chunk_impl(const gww_model* m, const Workspace& ws, int nc, f
   {  // conv1 (k=3, pad=1) + GELU : feats_tm [nc,3002,80] -> h1[:,1:,:]
     GemmCall g{};
     g.a_base = ws.feats_tm;
-    g.a_dims[0] = 80; g.a_dims[1] = 1; g.a_dims[2] = 3002; g.a_dims[3] = nc;
-    g.a_strides[0] = 160; g.a_strides[1] = 160; g.a_strides[2] = 3002ull * 160;
-    g.w_base = m->conv1_w; g.ktot = 384;
+    // time-major features: the three 80-channel rows t-1, t, t+1 of an output row are CONTIGUOUS (240 elements from
+    // padded row t), so the im2col operand is a tensor map whose row stride (80 elements) is smaller than its row
+    // length (240): K = 240 -> 4 k-blocks (columns 240..255 out of range = zero) instead of three taps x 128
+    // (VERDICT r1 5c without replicating the features).  GWW_CONV1_PACKED=0: the three row-shifted boxes of round 1.
+    static const bool packed = !(getenv("GWW_CONV1_PACKED") && atoi(getenv("GWW_CONV1_PACKED")) == 0);
+    if (packed) {
+      g.a_dims[0] = 240; g.a_dims[1] = 1; g.a_dims[2] = 3000; g.a_dims[3] = nc;
+      g.a_strides[0] = 160; g.a_strides[1] = 160; g.a_strides[2] = 3002ull * 160;
+      g.w_base = m->conv1_wp; g.ktot = 256;
+      g.p.kb_per_tap = 4; g.p.taps = 1;
+    } else {
+      g.a_dims[0] = 80; g.a_dims[1] = 1; g.a_dims[2] = 3002; g.a_dims[3] = nc;
+      g.a_strides[0] = 160; g.a_strides[1] = 160; g.a_strides[2] = 3002ull * 160;
+      g.w_base = m->conv1_w; g.ktot = 384;
+      g.p.kb_per_tap = 2; g.p.taps = 3;
+    }
     g.c_base = h1 + d;
     g.c_strides[0] = (uint64_t)d * 2; g.c_strides[1] = 3001ull * d * 2;
-    g.p.rows = 3000; g.p.batch = nc; g.p.n = d; g.p.kb_per_tap = 2; g.p.taps = 3; g.p.p_mod = 1;
+    g.p.rows = 3000; g.p.batch = nc; g.p.n = d; g.p.p_mod = 1;
     g.p.bias = m->conv1_b; g.p.resid = nullptr; g.p.pos = nullptr;
     g.epi = EPI_BIAS_GELU_BF16; g.block_n = bn_d; g.kind = PK_GEMM_CONV1;
     GWW_TRY(run_gemm(g, stream));
