@@ -213,10 +213,10 @@ def test_glitch_small_multiclass_argmax():
 
 
 @pytest.mark.parametrize("env", [{"GWW_LN_FOLD": "0"}, {"GWW_ATTN_PERSIST": "0"}, {"GWW_ATTN_PERSIST": "0", "GWW_ATTN_NT": "2"},
-                                 {"GWW_GEMM_MC": "1"}, {"GWW_GEMM_MC": "2"}])
+                                 {"GWW_GEMM_MC": "1"}, {"GWW_GEMM_MC": "2"}, {"GWW_CONV1_PACKED": "0"}])
 def test_alternative_kernel_paths_agree(env, tmp_path):
     """The switches of INTEGRATION.md select other kernels for the same maths (stand-alone LayerNorm,
-    one-CTA-per-item attention, forced single-CTA / CTA-pair GEMMs).  They are read once per process, so the
+    one-CTA-per-item attention, forced single-CTA / CTA-pair GEMMs, the conv-stem conv1 as three row-shifted taps).  They are read once per process, so the
     alternative runs in a child process; its pooled encoder output must match the default path's within
     the bf16 tolerance (and both are held to the fp32 oracle by the tests above).  Default-init weights: with
     the spread-scaled set two valid bf16 roundings of the hidden state differ by ~6e-2 from EACH OTHER (each is
